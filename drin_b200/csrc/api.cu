@@ -1,0 +1,91 @@
+// extern "C" boundary of libdrin_b200.so (declared in include/drin_b200.h).
+#include "../../include/drin_b200.h"
+
+#include "engine.cuh"
+#include "kernels.cuh"
+#include <string.h>
+
+using namespace drin;
+
+extern "C" {
+
+const char* drin_last_error(void) { return drin::last_error(); }
+int drin_version(void) { return 100; }
+
+int drin_split_planes(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  return split_planes((cudaStream_t)stream, x, (bf16*)hi, (bf16*)lo, n);
+}
+
+int drin_gemm(int32_t layout, const void* a_hi, const void* a_lo, int32_t lda, const void* b_hi, const void* b_lo,
+              int32_t ldb, int64_t M, int32_t N, int64_t K, float* C, int32_t ldc, const float* bias, void* out_hi,
+              void* out_lo, int32_t ld_planes, int32_t ksplit, float* partial, int32_t reference, void* stream) {
+  if (layout < 0 || layout > 2) return fail(DRIN_ERR_ARG, "drin_gemm: bad layout %d", layout);
+  Operand A, B;
+  A.hi = (const bf16*)a_hi; A.lo = (const bf16*)a_lo; A.ld = lda;
+  B.hi = (const bf16*)b_hi; B.lo = (const bf16*)b_lo; B.ld = ldb;
+  if (layout == GEMM_TN) { A.rows = K; A.cols = (int)M; } else { A.rows = M; A.cols = (int)K; }
+  if (layout == GEMM_NT) { B.rows = N; B.cols = (int)K; } else { B.rows = K; B.cols = N; }
+  GemmEpilogue ep;
+  ep.C = C; ep.ldc = ldc; ep.bias = bias;
+  ep.out_hi = (bf16*)out_hi; ep.out_lo = (bf16*)out_lo; ep.ld_planes = ld_planes;
+  if (reference) return gemm_reference_simt((cudaStream_t)stream, (GemmLayout)layout, A, B, M, N, K, ep);
+  return gemm_tcgen05((cudaStream_t)stream, (GemmLayout)layout, A, B, M, N, K, ep, ksplit, partial);
+}
+
+void drin_gemm_debug_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes) { gemm_debug_set_mn_desc(lbo_bytes, sbo_bytes); }
+
+int drin_workspace_bytes(const drin_config* cfg, size_t* bytes) {
+  if (!cfg || !bytes) return fail(DRIN_ERR_ARG, "drin_workspace_bytes: null argument");
+  Workspace ws;
+  DRIN_TRY(plan_workspace(*cfg, nullptr, nullptr, ws));
+  *bytes = ws.bytes;
+  return DRIN_OK;
+}
+
+int drin_forward(const drin_config* cfg, const drin_inputs* in, const drin_params* params, void* workspace,
+                 size_t workspace_bytes, float* scores, void* stream) {
+  if (!cfg || !in || !params) return fail(DRIN_ERR_ARG, "drin_forward: null argument");
+  return forward(*cfg, *in, *params, workspace, workspace_bytes, scores, (cudaStream_t)stream);
+}
+
+int drin_frontend(const drin_config* cfg, const drin_inputs* in, float* span, float* mimean, float* epool,
+                  float* edges, void* stream) {
+  if (!cfg || !in) return fail(DRIN_ERR_ARG, "drin_frontend: null argument");
+  DRIN_TRY(check_config(*cfg));
+  const drin_config& c = *cfg;
+  FrontendArgs fa{};
+  fa.B = c.batch; fa.C = c.candidates; fa.Lm = c.mention_tokens; fa.Le = c.entity_tokens; fa.P = c.regions;
+  fa.Om = c.mention_objects; fa.Oe = c.entity_objects; fa.D = c.embed_dim; fa.R = c.resnet_dim;
+  fa.mtf = in->mention_text_feature; fa.start = (const long long*)in->mention_start_pos;
+  fa.end = (const long long*)in->mention_end_pos; fa.mif = in->mention_image_feature;
+  fa.mof = in->mention_object_feature; fa.mos = in->mention_object_score; fa.etf = in->entity_text_feature;
+  fa.emask = (const long long*)in->entity_text_mask; fa.eif = in->entity_image_feature;
+  fa.eof = in->entity_object_feature; fa.eos = in->entity_object_score; fa.miet = in->miet_similarity;
+  fa.mtei = in->mtei_similarity;
+  fa.span_f = span; fa.mim_f = mimean; fa.ep_f = epool; fa.edges = edges;
+  return frontend((cudaStream_t)stream, fa, c.precision == DRIN_BF16);
+}
+
+// Test hook: device pointer and shape of a named intermediate inside a planned workspace.
+int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name, int32_t layer, void** ptr,
+                      int64_t* rows, int64_t* cols) {
+  if (!cfg || !name || !ptr || !rows || !cols) return fail(DRIN_ERR_ARG, "drin_debug_buffer: null argument");
+  Workspace ws;
+  DRIN_TRY(plan_workspace(*cfg, nullptr, workspace, ws));
+  const long long B = cfg->batch, BC = B * cfg->candidates, D = cfg->embed_dim;
+  if (layer < 0 || layer >= cfg->gcn_layers) return fail(DRIN_ERR_ARG, "drin_debug_buffer: bad layer");
+  const LayerWs& lw = ws.layer[layer];
+  if (!strcmp(name, "edges0")) { *ptr = ws.edges0; *rows = 4; *cols = BC; }
+  else if (!strcmp(name, "x0")) { *ptr = ws.x0; *rows = 2 * B + 2 * BC; *cols = D; }
+  else if (!strcmp(name, "h")) { *ptr = lw.h; *rows = lw.rows; *cols = D; }
+  else if (!strcmp(name, "xm")) { *ptr = lw.xm; *rows = 2 * B; *cols = D; }
+  else if (!strcmp(name, "fu")) { *ptr = lw.fu; *rows = 2 * B; *cols = D; }
+  else if (!strcmp(name, "g")) { *ptr = lw.g; *rows = 2 * B; *cols = D; }
+  else if (!strcmp(name, "edges_out")) { *ptr = lw.edges_out; *rows = 4; *cols = BC; }
+  else if (!strcmp(name, "dz")) { *ptr = ws.dz; *rows = 2 * B + 2 * BC; *cols = D; }
+  else return fail(DRIN_ERR_ARG, "drin_debug_buffer: unknown buffer '%s'", name);
+  if (!*ptr) return fail(DRIN_ERR_ARG, "drin_debug_buffer: '%s' is not allocated for this config/layer", name);
+  return DRIN_OK;
+}
+
+}  // extern "C"

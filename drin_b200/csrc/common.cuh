@@ -1,0 +1,80 @@
+// Shared device/host helpers for the drin_b200 sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace drin {
+
+// ---------------------------------------------------------------------------------------------
+// host: error reporting (C-ABI functions return an int status; text via drin_last_error())
+// ---------------------------------------------------------------------------------------------
+enum Status : int {
+  DRIN_OK = 0,
+  DRIN_ERR_ARG = 1,       // bad argument / unsupported shape
+  DRIN_ERR_CUDA = 2,      // CUDA runtime or driver error
+  DRIN_ERR_WORKSPACE = 3, // workspace too small
+};
+
+int fail(int code, const char* fmt, ...);   // records the message, returns `code`
+
+#define DRIN_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return ::drin::fail(::drin::DRIN_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, \
+                          cudaGetErrorString(e__));                                        \
+  } while (0)
+
+#define DRIN_LAUNCH_CHECK() DRIN_CUDA(cudaGetLastError())
+
+#define DRIN_TRY(expr)                 \
+  do {                                 \
+    int s__ = (expr);                  \
+    if (s__ != ::drin::DRIN_OK) return s__; \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// device: warp reductions and vector access
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit load (read-once inputs: keep them out of L1)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// split-bf16 representation of an fp32 value: x ~= hi + lo with |x - hi - lo| <= 2^-18 |x|
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// exact-erf GELU (F.gelu default) and its derivative
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+#endif  // __CUDACC__
+
+}  // namespace drin

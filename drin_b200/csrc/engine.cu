@@ -1,0 +1,237 @@
+// Workspace plan + forward orchestration of the DRIN hot path (reference drin/model.py:164-209).
+#include "engine.cuh"
+
+namespace drin {
+
+int check_config(const drin_config& c) {
+  if (c.batch <= 0 || c.candidates <= 1) return fail(DRIN_ERR_ARG, "config: batch=%d candidates=%d", c.batch, c.candidates);
+  if (c.embed_dim != 768) return fail(DRIN_ERR_ARG, "config: gcn_embed_dim=%d (kernels are built for 768)", c.embed_dim);
+  if (c.resnet_dim <= 0 || c.resnet_dim % 256) return fail(DRIN_ERR_ARG, "config: resnet_dim=%d must be a multiple of 256", c.resnet_dim);
+  if (c.gcn_layers < 1 || c.gcn_layers > DRIN_MAX_LAYERS) return fail(DRIN_ERR_ARG, "config: gcn_layers=%d (1..%d)", c.gcn_layers, DRIN_MAX_LAYERS);
+  if (c.mention_tokens <= 0 || c.regions <= 0 || c.entity_tokens < 0) return fail(DRIN_ERR_ARG, "config: bad token/region counts");
+  if (c.mention_objects < 1 || c.mention_objects > 4 || c.entity_objects < 1) return fail(DRIN_ERR_ARG, "config: mention_objects=%d entity_objects=%d", c.mention_objects, c.entity_objects);
+  if (c.precision != DRIN_FP32 && c.precision != DRIN_BF16) return fail(DRIN_ERR_ARG, "config: precision=%d", c.precision);
+  return DRIN_OK;
+}
+
+namespace {
+struct Bump {
+  char* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+  Planes planes(size_t n, bool split) {
+    Planes p;
+    p.hi = take<bf16>(n);
+    if (split) p.lo = take<bf16>(n);
+    return p;
+  }
+};
+}  // namespace
+
+int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Workspace& ws) {
+  DRIN_TRY(check_config(c));
+  const bool split = c.precision == DRIN_FP32;
+  const size_t B = c.batch, C = c.candidates, D = c.embed_dim, R = c.resnet_dim, BC = B * C;
+  const int L = c.gcn_layers;
+  Bump m(base);
+  ws.w_mt = m.planes(D * D, split);
+  ws.w_et = m.planes(D * D, split);
+  ws.w_mi = m.planes(D * R, split);
+  ws.w_ei = m.planes(D * R, split);
+  ws.span = m.planes(B * D, split);
+  ws.mim = m.planes(B * R, split);
+  if (split || c.entity_tokens > 0) {
+    ws.epool = m.planes(BC * D, split);
+  } else {   // bf16 WikiDiverse: the entity text rows are the GEMM operand as they are
+    ws.epool = Planes();
+    if (in) ws.epool.hi = const_cast<bf16*>(static_cast<const bf16*>(in->entity_text_feature));
+  }
+  if (split) {
+    ws.eimg = m.planes(BC * R, split);
+  } else {
+    ws.eimg = Planes();
+    if (in) ws.eimg.hi = const_cast<bf16*>(static_cast<const bf16*>(in->entity_image_feature));
+  }
+  ws.edges0 = m.take<float>(4 * BC);
+  ws.x0 = m.take<float>((2 * B + 2 * BC) * D);
+  ws.xm0_p = m.planes(2 * B * D, split);
+  for (int l = 0; l < L; ++l) {
+    LayerWs& lw = ws.layer[l];
+    lw.full = l < L - 1;
+    lw.rows = lw.full ? (long long)(2 * B + 2 * BC) : (long long)(B + BC);
+    lw.w_h = m.planes(D * D, split);
+    if (lw.full) {
+      lw.w_u = m.planes(D * D, split);
+      lw.w_v = m.planes(D * D, split);
+    }
+    if (l == 0) {
+      lw.xm = ws.x0;
+      lw.xm_p = ws.xm0_p;
+    } else {
+      lw.xm = m.take<float>(2 * B * D);
+      if (lw.full) lw.xm_p = m.planes(2 * B * D, split);
+    }
+    if (lw.full) {
+      lw.fu = m.take<float>(2 * B * D);
+      lw.fu_p = m.planes(2 * B * D, split);
+      lw.g = m.take<float>(2 * B * D);
+      lw.beta_u = m.take<float>(2 * B);
+      lw.edges_out = m.take<float>(4 * BC);
+    }
+    lw.z = m.planes((size_t)lw.rows * D, split);
+    lw.h = m.take<float>((size_t)lw.rows * D);
+  }
+  if (c.training) {
+    const size_t rows = 2 * B + 2 * BC;
+    ws.dh = m.planes(rows * D, split);
+    ws.dz = m.take<float>(rows * D);
+    ws.dxm = m.take<float>(2 * B * D);
+    ws.dxu = m.take<float>(2 * B * D);
+    ws.dg = m.take<float>(2 * B * D);
+    ws.dg_p = m.planes(2 * B * D, split);
+    ws.dbeta = m.take<float>(2 * B);
+    ws.dfu = m.take<float>(2 * B * D);
+    ws.dfu_p = m.planes(2 * B * D, split);
+    ws.dedges = m.take<float>(2 * 4 * BC);           // ping-pong between layers
+    ws.dx0 = m.planes(rows * D, split);
+    // split-K: enough slices to fill the machine for the [D, D] weight gradients (18 tiles each)
+    ws.ksplit = 8;
+    ws.partial = m.take<float>((size_t)ws.ksplit * D * (R > D ? R : D));
+    ws.colsum_ctas = 148 * 2;
+    ws.colsum = m.take<float>((size_t)2 * ws.colsum_ctas * 3 * D);
+  }
+  ws.bytes = align_up(m.off, 256);
+  return DRIN_OK;
+}
+
+static int split_weight(cudaStream_t s, const float* w, const Planes& p, size_t n) {
+  if (!w) return fail(DRIN_ERR_ARG, "null parameter pointer");
+  return split_planes(s, w, p.hi, p.lo, (long long)n);
+}
+
+static Operand op(const Planes& p, long long rows, int cols, long long row_offset = 0) {
+  Operand o;
+  o.hi = p.hi + row_offset * cols;
+  o.lo = p.lo ? p.lo + row_offset * cols : nullptr;
+  o.rows = rows;
+  o.cols = cols;
+  o.ld = cols;
+  return o;
+}
+
+int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace, size_t workspace_bytes,
+            float* scores, cudaStream_t stream) {
+  Workspace ws;
+  DRIN_TRY(plan_workspace(c, &in, workspace, ws));
+  if (!workspace || workspace_bytes < ws.bytes)
+    return fail(DRIN_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
+  if (!scores) return fail(DRIN_ERR_ARG, "scores is null");
+  const bool bf16_in = c.precision == DRIN_BF16;
+  const long long B = c.batch, C = c.candidates, BC = B * C;
+  const int D = c.embed_dim, R = c.resnet_dim, L = c.gcn_layers;
+
+  // ---- weights -> bf16 planes (they change every optimizer step) ----
+  DRIN_TRY(split_weight(stream, p.w_mt, ws.w_mt, (size_t)D * D));
+  DRIN_TRY(split_weight(stream, p.w_et, ws.w_et, (size_t)D * D));
+  DRIN_TRY(split_weight(stream, p.w_mi, ws.w_mi, (size_t)D * R));
+  DRIN_TRY(split_weight(stream, p.w_ei, ws.w_ei, (size_t)D * R));
+  for (int l = 0; l < L; ++l) {
+    DRIN_TRY(split_weight(stream, p.layer[l].w_h, ws.layer[l].w_h, (size_t)D * D));
+    if (ws.layer[l].full) {
+      DRIN_TRY(split_weight(stream, p.layer[l].w_u, ws.layer[l].w_u, (size_t)D * D));
+      DRIN_TRY(split_weight(stream, p.layer[l].w_v, ws.layer[l].w_v, (size_t)D * D));
+    }
+  }
+
+  // ---- front end: pooling, edges, projection operands ----
+  FrontendArgs fa{};
+  fa.B = c.batch; fa.C = c.candidates; fa.Lm = c.mention_tokens; fa.Le = c.entity_tokens; fa.P = c.regions;
+  fa.Om = c.mention_objects; fa.Oe = c.entity_objects; fa.D = D; fa.R = R;
+  fa.mtf = in.mention_text_feature; fa.start = (const long long*)in.mention_start_pos;
+  fa.end = (const long long*)in.mention_end_pos; fa.mif = in.mention_image_feature;
+  fa.mof = in.mention_object_feature; fa.mos = in.mention_object_score; fa.etf = in.entity_text_feature;
+  fa.emask = (const long long*)in.entity_text_mask; fa.eif = in.entity_image_feature;
+  fa.eof = in.entity_object_feature; fa.eos = in.entity_object_score; fa.miet = in.miet_similarity;
+  fa.mtei = in.mtei_similarity;
+  fa.span_hi = ws.span.hi; fa.span_lo = ws.span.lo; fa.mim_hi = ws.mim.hi; fa.mim_lo = ws.mim.lo;
+  const bool own_epool = !bf16_in || c.entity_tokens > 0;
+  fa.ep_hi = own_epool ? ws.epool.hi : nullptr; fa.ep_lo = own_epool ? ws.epool.lo : nullptr;
+  fa.ei_hi = bf16_in ? nullptr : ws.eimg.hi; fa.ei_lo = bf16_in ? nullptr : ws.eimg.lo;
+  fa.edges = ws.edges0;
+  DRIN_TRY(frontend(stream, fa, bf16_in));
+
+  // ---- input projections (ghmfc.py:66-69,250; model.py:42,45): x0 = [mt; mi; et; ei] ----
+  {
+    GemmEpilogue ep;
+    ep.ldc = D; ep.ld_planes = D;
+    ep.C = ws.x0; ep.bias = p.b_mt; ep.out_hi = ws.xm0_p.hi; ep.out_lo = ws.xm0_p.lo;
+    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.span, B, D), op(ws.w_mt, D, D), B, D, D, ep));
+    ep.C = ws.x0 + B * D; ep.bias = p.b_mi; ep.out_hi = ws.xm0_p.hi + B * D;
+    ep.out_lo = ws.xm0_p.lo ? ws.xm0_p.lo + B * D : nullptr;
+    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.mim, B, R), op(ws.w_mi, D, R), B, D, R, ep));
+    ep.out_hi = ep.out_lo = nullptr;
+    ep.C = ws.x0 + 2 * B * D; ep.bias = p.b_et;
+    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.epool, BC, D), op(ws.w_et, D, D), BC, D, D, ep));
+    ep.C = ws.x0 + (2 * B + BC) * D; ep.bias = p.b_ei;
+    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.eimg, BC, R), op(ws.w_ei, D, R), BC, D, R, ep));
+  }
+
+  // ---- GCN layers (model.py:205-206) ----
+  for (int l = 0; l < L; ++l) {
+    LayerWs& lw = ws.layer[l];
+    const drin_layer_params& lp = p.layer[l];
+    LayerFwdArgs la{};
+    la.B = c.batch; la.C = c.candidates; la.D = D; la.full = lw.full;
+    for (int k = 0; k < 4; ++k) la.en[k] = c.edge_enabled[k];
+    if (l == 0) {
+      la.x_et = ws.x0 + 2 * B * D;
+      la.x_ei = ws.x0 + (2 * B + BC) * D;
+      la.edges_in = ws.edges0;
+    } else {
+      const LayerWs& pw = ws.layer[l - 1];
+      const drin_layer_params& pp = p.layer[l - 1];
+      DRIN_TRY(mention_ln(stream, D, pw.h, 2 * B, pp.ln_w, pp.ln_b, lw.xm, lw.full ? lw.xm_p.hi : nullptr,
+                          lw.full ? lw.xm_p.lo : nullptr));
+      la.x_et = pw.h + 2 * B * D;
+      la.x_ei = pw.h + (2 * B + BC) * D;
+      la.ln_gamma = pp.ln_w;
+      la.ln_beta = pp.ln_b;
+      la.edges_in = pw.edges_out;
+    }
+    la.xm = lw.xm;
+    if (lw.full) {
+      GemmEpilogue ep;
+      ep.ldc = D; ep.ld_planes = D;
+      ep.C = lw.fu; ep.bias = lp.b_u; ep.out_hi = lw.fu_p.hi; ep.out_lo = lw.fu_p.lo;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.xm_p, 2 * B, D), op(lw.w_u, D, D), 2 * B, D, D, ep));
+      DRIN_TRY(rowdot(stream, D, lw.fu, 2 * B, lp.b_v, lw.beta_u));
+      GemmEpilogue eg;
+      eg.ldc = D; eg.C = lw.g;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(lw.fu_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, eg));
+      la.g = lw.g;
+      la.beta_u = lw.beta_u;
+      la.edges_out = lw.edges_out;
+    }
+    la.z_hi = lw.z.hi;
+    la.z_lo = lw.z.lo;
+    DRIN_TRY(gcn_layer_fwd(stream, la));
+    GemmEpilogue eh;
+    eh.ldc = D; eh.C = lw.h; eh.bias = lp.b_h;
+    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.z, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, eh));
+  }
+
+  // ---- candidate scoring (model.py:207-209) ----
+  const LayerWs& last = ws.layer[L - 1];
+  DRIN_TRY(score_fwd(stream, D, last.h, last.h + B * D, p.layer[L - 1].ln_w, p.layer[L - 1].ln_b, c.batch,
+                     c.candidates, scores));
+  return DRIN_OK;
+}
+
+}  // namespace drin

@@ -1,0 +1,63 @@
+// Workspace plan and forward/backward orchestration of the DRIN hot path.
+#pragma once
+#include "../../include/drin_b200.h"
+#include "kernels.cuh"
+
+namespace drin {
+
+struct Planes {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;   // null in bf16 mode
+};
+
+struct LayerWs {
+  bool full = false;
+  long long rows = 0;          // rows of z / h: full 2B+2BC (mt, mi, et, ei), last B+BC (mt, et)
+  Planes w_h, w_u, w_v;        // weight planes (w_u / w_v only for full layers)
+  float* xm = nullptr;         // [2B, D] activated mention vertices entering this layer (layer 0: alias of x0)
+  Planes xm_p;                 // planes of xm (full layers)
+  float* fu = nullptr;         // [2B, D] W_u xm + b_u
+  Planes fu_p;
+  float* g = nullptr;          // [2B, D] fu W_v
+  float* beta_u = nullptr;     // [2B]    fu . b_v
+  Planes z;                    // [rows, D] A operand of the W_h GEMM
+  float* h = nullptr;          // [rows, D] pre-LayerNorm output of W_h
+  float* edges_out = nullptr;  // [4, BC] (full)
+};
+
+struct Workspace {
+  size_t bytes = 0;
+  Planes w_mt, w_et, w_mi, w_ei;
+  Planes span, mim, epool, eimg;     // projection A operands
+  float* edges0 = nullptr;           // [4, BC]
+  float* x0 = nullptr;               // [2B+2BC, D] projection outputs (mt, mi, et, ei)
+  Planes xm0_p;                      // planes of the first 2B rows of x0
+  LayerWs layer[DRIN_MAX_LAYERS];
+  // ---- backward scratch ----
+  Planes dh;                         // [2B+2BC, D] gradient w.r.t. h (A of dZ GEMM, A of dW_h GEMM)
+  float* dz = nullptr;               // [2B+2BC, D]
+  float* dxm = nullptr;              // [2B, D] gradient w.r.t. activated mention vertices (partial)
+  float* dxu = nullptr;              // [2B, D] dfu W_u
+  float* dg = nullptr;               // [2B, D]
+  Planes dg_p;
+  float* dbeta = nullptr;            // [2B]
+  float* dfu = nullptr;              // [2B, D]
+  Planes dfu_p;
+  float* dedges = nullptr;           // [4, BC] gradient w.r.t. the edges entering the layer above
+  Planes dx0;                        // [2B+2BC, D] gradient w.r.t. projection outputs (A of projection dW GEMMs)
+  float* partial = nullptr;          // split-K partial sums
+  float* colsum = nullptr;           // per-CTA partial column sums (bias / LayerNorm gradients)
+  int colsum_ctas = 0;
+  int ksplit = 1;
+};
+
+int check_config(const drin_config& c);
+// Carve `base` (may be null: size query) into the buffers above.
+int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Workspace& ws);
+
+int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace, size_t workspace_bytes,
+            float* scores, cudaStream_t stream);
+int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,
+             size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream);
+
+}  // namespace drin

@@ -1,0 +1,498 @@
+// Backward of the fused GCN stages (mirrors gcn_fwd.cu; reference semantics: autograd through
+// drin/model.py:121-153,207-209).  Same warp-per-row layout; activated vertices are recomputed from
+// the saved pre-LayerNorm rows instead of being stored.
+//
+//   score_bwd            d(cosine score) -> dL/dh of the last layer (mention + candidate rows)
+//   gcn_layer_bwd        per mention: gradients of the message aggregation, the enable mask and the
+//                        dynamic edge update w.r.t. candidate vertices (then through LayerNorm+GELU of
+//                        the previous layer), mention vertices (partial), edges, g = fu W_v and beta
+//   mention_bwd_finish   mention rows: add the W_u path, LayerNorm+GELU backward
+//   dfu_finish           dfu = dg W_v^T + dbeta * b_v ; bias gradients of w_u / w_v
+//   colsum_reduce        deterministic reduction of per-CTA partial column sums (bias / LayerNorm grads)
+//
+// Partial sums live in per-warp shared-memory slices and are reduced in a fixed order, so gradients are
+// bit-reproducible run to run.
+#include "kernels.cuh"
+#include "rows.cuh"
+
+namespace drin {
+
+static constexpr int BW_NW = 4;           // warps per CTA in the backward kernels
+static constexpr int BW_CTAS = 148 * 2;   // persistent grid (must match Workspace::colsum_ctas)
+
+template <int D>
+__device__ __forceinline__ void row_zero_smem(float* s, int lane) {
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) *reinterpret_cast<float4*>(s + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// write the CTA's partial column sums: out[(cta * nvec + v) * D + col] = sum_w part[v][w][col]
+template <int D, int NW>
+__device__ __forceinline__ void flush_partials(const float* s_part, int nvec, float* out, int tid) {
+  for (int i = tid; i < nvec * D; i += NW * 32) {
+    const int v = i / D, col = i - v * D;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += s_part[(v * NW + w) * D + col];
+    out[((long long)blockIdx.x * nvec + v) * D + col] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// score_bwd
+// ---------------------------------------------------------------------------------------------
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32) score_bwd_kernel(const ScoreBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_gamma = sm;
+  float* s_beta = s_gamma + D;
+  float* s_m = s_beta + D;                 // activated mention row
+  float* s_dam = s_m + D;                  // [NW][D] per-warp dL/da_m (vector part)
+  float* s_part = s_dam + NW * D;          // [3][NW][D]: dgamma, dbeta, db_h
+  __shared__ float s_mnorm;
+  __shared__ float s_coef[NW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += NW * 32) {
+    s_gamma[i] = a.gamma[i];
+    s_beta[i] = a.beta[i];
+  }
+  for (int i = tid; i < 3 * NW * D; i += NW * 32) s_part[i] = 0.f;
+  float* pg = s_part + (0 * NW + warp) * D;
+  float* pb = s_part + (1 * NW + warp) * D;
+  float* ph = s_part + (2 * NW + warp) * D;
+  const long long B = a.B;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    __syncthreads();
+    if (warp == 0) {
+      RowT<D> m;
+      row_load<D>(m, a.h_mt + (long long)b * D, lane);
+      row_ln_gelu<D>(m, s_gamma, s_beta, lane);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < RowT<D>::NV * 4; ++i) q += m.v[i] * m.v[i];
+      q = warp_sum(q);
+      row_store<D>(m, s_m, lane);
+      if (lane == 0) s_mnorm = fmaxf(sqrtf(q), 1e-8f);
+    }
+    row_zero_smem<D>(s_dam + warp * D, lane);
+    float coef = 0.f;
+    __syncthreads();
+    const float nm = s_mnorm;
+    for (int c = warp; c < a.C; c += NW) {
+      const long long r = (long long)b * a.C + c;
+      RowT<D> h, e;
+      row_load<D>(h, a.h_et + r * D, lane);
+      e = h;
+      row_ln_gelu<D>(e, s_gamma, s_beta, lane);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < RowT<D>::NV * 4; ++i) q += e.v[i] * e.v[i];
+      q = warp_sum(q);
+      const float ne = fmaxf(sqrtf(q), 1e-8f);
+      const float cs = warp_sum(row_dot<D>(e, s_m, lane)) / (nm * ne);
+      const float ds = a.dscores[r];
+      const float w1 = ds / (nm * ne), w2 = ds * cs / (ne * ne);
+      coef += ds * cs / (nm * nm);
+      // dL/da_e = w1 * a_m - w2 * a_e ; dL/da_m += w1 * a_e
+#pragma unroll
+      for (int j = 0; j < RowT<D>::NV; ++j) {
+        const int off = (j * 32 + lane) * 4;
+        const float4 mv = *reinterpret_cast<const float4*>(s_m + off);
+        float4 acc = *reinterpret_cast<float4*>(s_dam + warp * D + off);
+        acc.x += w1 * e.v[4 * j]; acc.y += w1 * e.v[4 * j + 1]; acc.z += w1 * e.v[4 * j + 2]; acc.w += w1 * e.v[4 * j + 3];
+        *reinterpret_cast<float4*>(s_dam + warp * D + off) = acc;
+        e.v[4 * j] = w1 * mv.x - w2 * e.v[4 * j];
+        e.v[4 * j + 1] = w1 * mv.y - w2 * e.v[4 * j + 1];
+        e.v[4 * j + 2] = w1 * mv.z - w2 * e.v[4 * j + 2];
+        e.v[4 * j + 3] = w1 * mv.w - w2 * e.v[4 * j + 3];
+      }
+      row_ln_gelu_bwd<D>(h, e, s_gamma, s_beta, pg, pb, lane);
+      row_accum_smem<D>(e, ph, lane);
+      const long long zr = B + r;
+      row_store_planes<D>(e, a.dh_hi + zr * D, a.dh_lo ? a.dh_lo + zr * D : nullptr, lane);
+    }
+    if (lane == 0) s_coef[warp] = coef;
+    __syncthreads();
+    if (warp == 0) {
+      float ctot = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) ctot += s_coef[w];
+      RowT<D> d, h;
+#pragma unroll
+      for (int j = 0; j < RowT<D>::NV; ++j) {
+        const int off = (j * 32 + lane) * 4;
+        const float4 mv = *reinterpret_cast<const float4*>(s_m + off);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const float4 u = *reinterpret_cast<const float4*>(s_dam + w * D + off);
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        d.v[4 * j] = t.x - ctot * mv.x;
+        d.v[4 * j + 1] = t.y - ctot * mv.y;
+        d.v[4 * j + 2] = t.z - ctot * mv.z;
+        d.v[4 * j + 3] = t.w - ctot * mv.w;
+      }
+      row_load<D>(h, a.h_mt + (long long)b * D, lane);
+      row_ln_gelu_bwd<D>(h, d, s_gamma, s_beta, pg, pb, lane);
+      row_accum_smem<D>(d, ph, lane);
+      row_store_planes<D>(d, a.dh_hi + (long long)b * D, a.dh_lo ? a.dh_lo + (long long)b * D : nullptr, lane);
+    }
+  }
+  __syncthreads();
+  flush_partials<D, NW>(s_part, 3, a.partials, tid);
+}
+
+int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a) {
+  if (a.D != 768) return fail(DRIN_ERR_ARG, "score_bwd: gcn_embed_dim %d not built (768 only)", a.D);
+  constexpr int D = 768;
+  const size_t smem = (size_t)(3 + BW_NW + 3 * BW_NW) * D * sizeof(float);
+  DRIN_CUDA(cudaFuncSetAttribute(score_bwd_kernel<D, BW_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_bwd_kernel<D, BW_NW><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gcn_layer_bwd
+// ---------------------------------------------------------------------------------------------
+template <int D, int NW, bool FULL>
+__global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_xmt = sm;                       // activated mention vertices of this layer
+  float* s_xmi = s_xmt + D;
+  float* s_dzmt = s_xmi + D;               // dL/dz of the mention rows
+  float* s_dzmi = s_dzmt + D;
+  float* s_gmt = s_dzmi + D;               // g = fu W_v (FULL)
+  float* s_gmi = s_gmt + D;
+  float* s_gamma = s_gmi + D;
+  float* s_beta = s_gamma + D;
+  float* s_acc = s_beta + D;               // [4][NW][D]: A_mt, A_mi, G_mt, G_mi
+  float* s_part = s_acc + 4 * NW * D;      // [3][NW][D]
+  __shared__ float s_db[2][NW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long B = a.B, BC = (long long)a.B * a.C;
+  const bool ln = a.ln_gamma != nullptr;
+  if (ln) {
+    for (int i = tid; i < D; i += NW * 32) {
+      s_gamma[i] = a.ln_gamma[i];
+      s_beta[i] = a.ln_beta[i];
+    }
+  }
+  for (int i = tid; i < 3 * NW * D; i += NW * 32) s_part[i] = 0.f;
+  float* p0 = s_part + (0 * NW + warp) * D;
+  float* p1 = s_part + (1 * NW + warp) * D;
+  float* p2 = s_part + (2 * NW + warp) * D;
+  float* accA_mt = s_acc + (0 * NW + warp) * D;
+  float* accA_mi = s_acc + (1 * NW + warp) * D;
+  float* accG_mt = s_acc + (2 * NW + warp) * D;
+  float* accG_mi = s_acc + (3 * NW + warp) * D;
+  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+  // row offsets of the dz blocks for this layer's layout
+  const float* dz_mt = a.dz;
+  const float* dz_mi = FULL ? a.dz + B * D : nullptr;
+  const float* dz_et = a.dz + (FULL ? 2 * B : B) * D;
+  const float* dz_ei = FULL ? a.dz + (2 * B + BC) * D : nullptr;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < D; i += NW * 32) {
+      s_xmt[i] = a.xm[(long long)b * D + i];
+      s_xmi[i] = a.xm[(B + b) * D + i];
+      s_dzmt[i] = dz_mt[(long long)b * D + i];
+      s_dzmi[i] = FULL ? dz_mi[(long long)b * D + i] : 0.f;
+      if (FULL) {
+        s_gmt[i] = a.g[(long long)b * D + i];
+        s_gmi[i] = a.g[(B + b) * D + i];
+      }
+    }
+    row_zero_smem<D>(accA_mt, lane);
+    row_zero_smem<D>(accA_mi, lane);
+    if (FULL) {
+      row_zero_smem<D>(accG_mt, lane);
+      row_zero_smem<D>(accG_mi, lane);
+    }
+    float dbeta_mt = 0.f, dbeta_mi = 0.f;
+    __syncthreads();
+
+    for (int c = warp; c < a.C; c += NW) {
+      const long long r = (long long)b * a.C + c;
+      RowT<D> xet, xei, det, dei;
+      row_load<D>(xet, a.x_et + r * D, lane);
+      row_load<D>(xei, a.x_ei + r * D, lane);
+      if (ln) {
+        row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
+        row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
+      }
+      row_load<D>(det, dz_et + r * D, lane);
+      if (FULL) row_load<D>(dei, dz_ei + r * D, lane);
+      const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
+      const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
+      // dot products for the edge gradients
+      float pd0 = row_dot<D>(xet, s_dzmt, lane), pd1 = row_dot<D>(xei, s_dzmt, lane);
+      float q0 = row_dot<D>(det, s_xmt, lane), q2 = row_dot<D>(det, s_xmi, lane);
+      float pd2 = 0.f, pd3 = 0.f, q1 = 0.f, q3 = 0.f;
+      if (FULL) {
+        pd2 = row_dot<D>(xet, s_dzmi, lane);
+        pd3 = row_dot<D>(xei, s_dzmi, lane);
+        q1 = row_dot<D>(dei, s_xmt, lane);
+        q3 = row_dot<D>(dei, s_xmi, lane);
+      }
+      pd0 = warp_sum(pd0); pd1 = warp_sum(pd1); q0 = warp_sum(q0); q2 = warp_sum(q2);
+      if (FULL) { pd2 = warp_sum(pd2); pd3 = warp_sum(pd3); q1 = warp_sum(q1); q3 = warp_sum(q3); }
+      float de0 = pd0 * invC + q0, de1 = pd1 * invC + q1, de2 = pd2 * invC + q2, de3 = pd3 * invC + q3;
+      float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
+      if (FULL) {
+        const float o0 = a.edges_out[r], o1 = a.edges_out[BC + r], o2 = a.edges_out[2 * BC + r], o3 = a.edges_out[3 * BC + r];
+        ds0 = a.dedges_out[r] * o0 * (1.f - o0);
+        ds1 = a.dedges_out[BC + r] * o1 * (1.f - o1);
+        ds2 = a.dedges_out[2 * BC + r] * o2 * (1.f - o2);
+        ds3 = a.dedges_out[3 * BC + r] * o3 * (1.f - o3);
+        de0 += ds0; de1 += ds1; de2 += ds2; de3 += ds3;
+        dbeta_mt += (ds0 + ds1) * invD;
+        dbeta_mi += (ds2 + ds3) * invD;
+      }
+      if (a.dedges_in && lane == 0) {
+        a.dedges_in[r] = de0 * a.en[0];
+        a.dedges_in[BC + r] = de1 * a.en[1];
+        a.dedges_in[2 * BC + r] = de2 * a.en[2];
+        a.dedges_in[3 * BC + r] = de3 * a.en[3];
+      }
+      // accumulators and candidate-row gradients
+#pragma unroll
+      for (int j = 0; j < RowT<D>::NV; ++j) {
+        const int off = (j * 32 + lane) * 4;
+        float4 amt = *reinterpret_cast<float4*>(accA_mt + off);
+        float4 ami = *reinterpret_cast<float4*>(accA_mi + off);
+        const float4 zmt = *reinterpret_cast<const float4*>(s_dzmt + off);
+        const float4 zmi = *reinterpret_cast<const float4*>(s_dzmi + off);
+        const float zm[4] = {zmt.x, zmt.y, zmt.z, zmt.w}, zi[4] = {zmi.x, zmi.y, zmi.z, zmi.w};
+        float* amtp = reinterpret_cast<float*>(&amt);
+        float* amip = reinterpret_cast<float*>(&ami);
+        float4 gmt4 = make_float4(0.f, 0.f, 0.f, 0.f), gmi4 = gmt4, Gmt = gmt4, Gmi = gmt4;
+        if (FULL) {
+          gmt4 = *reinterpret_cast<const float4*>(s_gmt + off);
+          gmi4 = *reinterpret_cast<const float4*>(s_gmi + off);
+          Gmt = *reinterpret_cast<float4*>(accG_mt + off);
+          Gmi = *reinterpret_cast<float4*>(accG_mi + off);
+        }
+        const float gm[4] = {gmt4.x, gmt4.y, gmt4.z, gmt4.w}, gi[4] = {gmi4.x, gmi4.y, gmi4.z, gmi4.w};
+        float* Gmtp = reinterpret_cast<float*>(&Gmt);
+        float* Gmip = reinterpret_cast<float*>(&Gmi);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * j + k;
+          const float dze = det.v[i], dzi = FULL ? dei.v[i] : 0.f;
+          amtp[k] += e0 * dze + e1 * dzi;
+          amip[k] += e2 * dze + e3 * dzi;
+          if (FULL) {
+            Gmtp[k] += (ds0 * xet.v[i] + ds1 * xei.v[i]) * invD;
+            Gmip[k] += (ds2 * xet.v[i] + ds3 * xei.v[i]) * invD;
+          }
+          det.v[i] = dze + (e0 * zm[k] + e2 * zi[k]) * invC + (ds0 * gm[k] + ds2 * gi[k]) * invD;
+          dei.v[i] = dzi + (e1 * zm[k] + e3 * zi[k]) * invC + (ds1 * gm[k] + ds3 * gi[k]) * invD;
+        }
+        *reinterpret_cast<float4*>(accA_mt + off) = amt;
+        *reinterpret_cast<float4*>(accA_mi + off) = ami;
+        if (FULL) {
+          *reinterpret_cast<float4*>(accG_mt + off) = Gmt;
+          *reinterpret_cast<float4*>(accG_mi + off) = Gmi;
+        }
+      }
+      const long long r_et = 2 * B + r, r_ei = 2 * B + BC + r;      // rows in the [mt; mi; et; ei] layout
+      if (ln) {
+        RowT<D> h;
+        row_load<D>(h, a.x_et + r * D, lane);
+        row_ln_gelu_bwd<D>(h, det, s_gamma, s_beta, p0, p1, lane);
+        row_accum_smem<D>(det, p2, lane);
+        row_load<D>(h, a.x_ei + r * D, lane);
+        row_ln_gelu_bwd<D>(h, dei, s_gamma, s_beta, p0, p1, lane);
+        row_accum_smem<D>(dei, p2, lane);
+      } else {
+        row_accum_smem<D>(det, p0, lane);       // db_et
+        row_accum_smem<D>(dei, p1, lane);       // db_ei
+      }
+      row_store_planes<D>(det, a.dcand_hi + r_et * D, a.dcand_lo ? a.dcand_lo + r_et * D : nullptr, lane);
+      row_store_planes<D>(dei, a.dcand_hi + r_ei * D, a.dcand_lo ? a.dcand_lo + r_ei * D : nullptr, lane);
+    }
+    if (lane == 0) {
+      s_db[0][warp] = dbeta_mt;
+      s_db[1][warp] = dbeta_mi;
+    }
+    __syncthreads();
+    // mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
+    for (int i = tid; i < 2 * D; i += NW * 32) {
+      const int which = i / D, col = i - which * D;
+      float t = which ? s_dzmi[col] : s_dzmt[col];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += s_acc[(which * NW + w) * D + col];
+      a.dxm[(which ? B + b : (long long)b) * D + col] = t;
+      if (FULL) {
+        float gsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) gsum += s_acc[((2 + which) * NW + w) * D + col];
+        bf16 hh, ll;
+        split_bf16(gsum, hh, ll);
+        const long long gr = (which ? B + b : (long long)b) * D + col;
+        a.dg_hi[gr] = hh;
+        if (a.dg_lo) a.dg_lo[gr] = ll;
+      }
+    }
+    if (FULL && tid < 2) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += s_db[tid][w];
+      a.dbeta[tid ? B + b : (long long)b] = t;
+    }
+  }
+  __syncthreads();
+  flush_partials<D, NW>(s_part, 3, a.partials, tid);
+}
+
+int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
+  if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
+  constexpr int D = 768;
+  const size_t smem = (size_t)(8 + 7 * BW_NW) * D * sizeof(float);
+  if (a.full) {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcn_layer_bwd_kernel<D, BW_NW, true><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
+  } else {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcn_layer_bwd_kernel<D, BW_NW, false><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
+  }
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mention_bwd_finish: rows of the 2B mention vertices
+// ---------------------------------------------------------------------------------------------
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32) mention_bwd_finish_kernel(const MentionBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_gamma = sm;
+  float* s_beta = s_gamma + D;
+  float* s_part = s_beta + D;              // [3][NW][D]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool ln = a.ln_gamma != nullptr;
+  if (ln) {
+    for (int i = tid; i < D; i += NW * 32) {
+      s_gamma[i] = a.ln_gamma[i];
+      s_beta[i] = a.ln_beta[i];
+    }
+  }
+  for (int i = tid; i < 3 * NW * D; i += NW * 32) s_part[i] = 0.f;
+  __syncthreads();
+  float* p0 = s_part + (0 * NW + warp) * D;
+  float* p1 = s_part + (1 * NW + warp) * D;
+  float* p2 = s_part + (2 * NW + warp) * D;
+  const long long rows = 2LL * a.B;
+  for (long long r = (long long)blockIdx.x * NW + warp; r < rows; r += (long long)gridDim.x * NW) {
+    RowT<D> d;
+    row_load<D>(d, a.dxm + r * D, lane);
+    if (a.dxu) {
+      RowT<D> u;
+      row_load<D>(u, a.dxu + r * D, lane);
+#pragma unroll
+      for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] += u.v[i];
+    }
+    if (ln) {
+      RowT<D> h;
+      row_load<D>(h, a.h_prev + r * D, lane);
+      row_ln_gelu_bwd<D>(h, d, s_gamma, s_beta, p0, p1, lane);
+      row_accum_smem<D>(d, p2, lane);
+    } else {
+      row_accum_smem<D>(d, r < a.B ? p0 : p1, lane);      // db_mt / db_mi
+    }
+    row_store_planes<D>(d, a.out_hi + r * D, a.out_lo ? a.out_lo + r * D : nullptr, lane);
+  }
+  __syncthreads();
+  flush_partials<D, NW>(s_part, 3, a.partials, tid);
+}
+
+int mention_bwd_finish(cudaStream_t stream, const MentionBwdArgs& a) {
+  if (a.D != 768) return fail(DRIN_ERR_ARG, "mention_bwd_finish: gcn_embed_dim %d not built (768 only)", a.D);
+  constexpr int D = 768;
+  const size_t smem = (size_t)(2 + 3 * BW_NW) * D * sizeof(float);
+  mention_bwd_finish_kernel<D, BW_NW><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dfu_finish: dfu = dfu_raw + dbeta * b_v (in place + planes); partials: db_u = sum dfu, db_v = sum dbeta * fu
+// ---------------------------------------------------------------------------------------------
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32) dfu_finish_kernel(float* __restrict__ dfu, const float* __restrict__ dbeta,
+                                                              const float* __restrict__ b_v,
+                                                              const float* __restrict__ fu, long long rows,
+                                                              bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                                                              float* __restrict__ partials) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_bv = sm;
+  float* s_part = s_bv + D;                // [2][NW][D]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += NW * 32) s_bv[i] = b_v[i];
+  for (int i = tid; i < 2 * NW * D; i += NW * 32) s_part[i] = 0.f;
+  __syncthreads();
+  float* p0 = s_part + (0 * NW + warp) * D;
+  float* p1 = s_part + (1 * NW + warp) * D;
+  for (long long r = (long long)blockIdx.x * NW + warp; r < rows; r += (long long)gridDim.x * NW) {
+    RowT<D> d, f;
+    row_load<D>(d, dfu + r * D, lane);
+    row_load<D>(f, fu + r * D, lane);
+    const float db = dbeta[r];
+#pragma unroll
+    for (int j = 0; j < RowT<D>::NV; ++j) {
+      const float4 bv = *reinterpret_cast<const float4*>(s_bv + (j * 32 + lane) * 4);
+      d.v[4 * j] += db * bv.x; d.v[4 * j + 1] += db * bv.y; d.v[4 * j + 2] += db * bv.z; d.v[4 * j + 3] += db * bv.w;
+      f.v[4 * j] *= db; f.v[4 * j + 1] *= db; f.v[4 * j + 2] *= db; f.v[4 * j + 3] *= db;
+    }
+    row_accum_smem<D>(d, p0, lane);
+    row_accum_smem<D>(f, p1, lane);
+    row_store<D>(d, dfu + r * D, lane);
+    row_store_planes<D>(d, out_hi + r * D, out_lo ? out_lo + r * D : nullptr, lane);
+  }
+  __syncthreads();
+  flush_partials<D, NW>(s_part, 2, partials, tid);
+}
+
+int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const float* b_v, const float* fu,
+               long long rows, bf16* out_hi, bf16* out_lo, float* partials) {
+  if (D != 768) return fail(DRIN_ERR_ARG, "dfu_finish: gcn_embed_dim %d not built (768 only)", D);
+  const size_t smem = (size_t)(1 + 2 * BW_NW) * 768 * sizeof(float);
+  dfu_finish_kernel<768, BW_NW><<<BW_CTAS, BW_NW * 32, smem, stream>>>(dfu, dbeta, b_v, fu, rows, out_hi, out_lo,
+                                                                       partials);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// colsum_reduce: out_v[col] = sum over sources and CTAs of partials[(cta * nvec + v) * D + col]
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_reduce_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int ctas, int nvec,
+                                     int D, float* out0, float* out1, float* out2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec * D) return;
+  const int v = i / D, col = i - v * D;
+  float* out = v == 0 ? out0 : (v == 1 ? out1 : out2);
+  if (!out) return;
+  float t = 0.f;
+  for (int c = 0; c < ctas; ++c) t += src0[((long long)c * nvec + v) * D + col];
+  if (src1)
+    for (int c = 0; c < ctas; ++c) t += src1[((long long)c * nvec + v) * D + col];
+  out[col] = t;
+}
+
+int colsum_reduce(cudaStream_t stream, const float* src0, const float* src1, int nvec, int D, float* out0, float* out1,
+                  float* out2) {
+  const int n = nvec * D;
+  colsum_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(src0, src1, BW_CTAS, nvec, D, out0, out1, out2);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+int backward_ctas() { return BW_CTAS; }
+
+}  // namespace drin

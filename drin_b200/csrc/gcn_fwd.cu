@@ -1,0 +1,280 @@
+// Fused memory-bound forward stages of the GCN (reference drin/model.py:121-153, 207-209).
+//
+// The dense work of a layer is three GEMMs (gemm_tcgen05.cu); everything around them is fused here so
+// every vertex row (768 fp32 = 3 KB) is read once per layer:
+//
+//   gcn_layer_fwd   per mention: enable mask (model.py:122), message aggregation for all four vertex
+//                   types (model.py:124-127,139-146), the dynamic edge update
+//                   e' = sigmoid(mean_D(W_u u * W_v v) + e) (model.py:131-134,148-153) and the split-bf16
+//                   A operand z = agg + x of the shared W_h GEMM (model.py:128).
+//                   LayerNorm + GELU of the PREVIOUS layer (model.py:128) is applied on the fly when the
+//                   candidate rows are read, so activated vertices are never written to HBM.
+//   mention_ln      LayerNorm + GELU of the 2B mention rows (they feed the small W_u GEMM).
+//   score           final LayerNorm + GELU + cosine candidate scoring (model.py:207-209).
+//
+// Edge update without the big W_v GEMM: mean_D(fu_b * (W_v v + b_v)) = (v . (fu_b W_v) + fu_b . b_v) / D,
+// so only g_b = fu_b W_v (2B rows) goes through the tensor cores and each candidate costs 4 dot products.
+//
+// Layout: a warp owns one vertex row; lane l holds elements (j*32 + l)*4 .. +3, j < D/128, i.e. every
+// load/store is a fully coalesced 512-B warp transaction.  Row statistics use warp shuffles.
+#include "kernels.cuh"
+#include "rows.cuh"
+
+namespace drin {
+
+// ---------------------------------------------------------------------------------------------
+// gcn_layer_fwd
+// ---------------------------------------------------------------------------------------------
+template <int D, int NW, bool FULL>
+__global__ void __launch_bounds__(NW * 32) gcn_layer_fwd_kernel(const LayerFwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_mt = sm;                 // [D] mention text vertex (layer input)
+  float* s_mi = s_mt + D;           // [D] mention image vertex
+  float* s_gmt = s_mi + D;          // [D] g = fu W_v for u = mt   (FULL)
+  float* s_gmi = s_gmt + D;         // [D]                u = mi   (FULL)
+  float* s_gamma = s_gmi + D;       // [D] LayerNorm of the previous layer (if a.ln_gamma)
+  float* s_beta = s_gamma + D;      // [D]
+  float* s_acc = s_beta + D;        // [2][NW][D] per-warp partial aggregates
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long B = a.B, BC = (long long)a.B * a.C;
+  const bool ln = a.ln_gamma != nullptr;
+  if (ln) {
+    for (int i = tid; i < D; i += NW * 32) {
+      s_gamma[i] = a.ln_gamma[i];
+      s_beta[i] = a.ln_beta[i];
+    }
+  }
+  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    __syncthreads();                                        // previous mention done with smem
+    for (int i = tid; i < D; i += NW * 32) {
+      s_mt[i] = a.xm[(long long)b * D + i];
+      s_mi[i] = a.xm[(B + b) * D + i];
+      if (FULL) {
+        s_gmt[i] = a.g[(long long)b * D + i];
+        s_gmi[i] = a.g[(B + b) * D + i];
+      }
+    }
+    __syncthreads();
+    const float beta_mt = FULL ? a.beta_u[b] : 0.f;
+    const float beta_mi = FULL ? a.beta_u[B + b] : 0.f;
+
+    RowT<D> amt, ami;                                       // per-warp partial message sums
+#pragma unroll
+    for (int i = 0; i < RowT<D>::NV * 4; ++i) { amt.v[i] = 0.f; ami.v[i] = 0.f; }
+
+    for (int c = warp; c < a.C; c += NW) {
+      const long long r = (long long)b * a.C + c;
+      RowT<D> xet, xei;
+      row_load<D>(xet, a.x_et + r * D, lane);
+      row_load<D>(xei, a.x_ei + r * D, lane);
+      if (ln) {
+        row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
+        row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
+      }
+      const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
+      const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
+      if (FULL) {
+        // dynamic edge update (model.py:131-134,148-153): u in {mt, mi}, v in {et, ei}
+        float d0 = row_dot<D>(xet, s_gmt, lane), d1 = row_dot<D>(xei, s_gmt, lane);
+        float d2 = row_dot<D>(xet, s_gmi, lane), d3 = row_dot<D>(xei, s_gmi, lane);
+        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
+        if (lane == 0) {
+          a.edges_out[r] = 1.0f / (1.0f + __expf(-((d0 + beta_mt) * invD + e0)));
+          a.edges_out[BC + r] = 1.0f / (1.0f + __expf(-((d1 + beta_mt) * invD + e1)));
+          a.edges_out[2 * BC + r] = 1.0f / (1.0f + __expf(-((d2 + beta_mi) * invD + e2)));
+          a.edges_out[3 * BC + r] = 1.0f / (1.0f + __expf(-((d3 + beta_mi) * invD + e3)));
+        }
+      }
+      // messages to the mention vertices (mean over ALL C slots, model.py:144)
+#pragma unroll
+      for (int i = 0; i < RowT<D>::NV * 4; ++i) {
+        amt.v[i] += e0 * xet.v[i] + e1 * xei.v[i];
+        if (FULL) ami.v[i] += e2 * xet.v[i] + e3 * xei.v[i];
+      }
+      // z = x + message for the entity vertices (model.py:146,128)
+      RowT<D> z;
+#pragma unroll
+      for (int j = 0; j < RowT<D>::NV; ++j) {
+        const float4 mt = *reinterpret_cast<const float4*>(s_mt + (j * 32 + lane) * 4);
+        const float4 mi = *reinterpret_cast<const float4*>(s_mi + (j * 32 + lane) * 4);
+        z.v[4 * j] = xet.v[4 * j] + e0 * mt.x + e2 * mi.x;
+        z.v[4 * j + 1] = xet.v[4 * j + 1] + e0 * mt.y + e2 * mi.y;
+        z.v[4 * j + 2] = xet.v[4 * j + 2] + e0 * mt.z + e2 * mi.z;
+        z.v[4 * j + 3] = xet.v[4 * j + 3] + e0 * mt.w + e2 * mi.w;
+        if (FULL) {
+          xei.v[4 * j] += e1 * mt.x + e3 * mi.x;
+          xei.v[4 * j + 1] += e1 * mt.y + e3 * mi.y;
+          xei.v[4 * j + 2] += e1 * mt.z + e3 * mi.z;
+          xei.v[4 * j + 3] += e1 * mt.w + e3 * mi.w;
+        }
+      }
+      const long long zr_et = (FULL ? 2 * B : B) + r;
+      row_store_planes<D>(z, a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane);
+      if (FULL) {
+        const long long zr_ei = 2 * B + BC + r;
+        row_store_planes<D>(xei, a.z_hi + zr_ei * D, a.z_lo ? a.z_lo + zr_ei * D : nullptr, lane);
+      }
+    }
+    // cross-warp reduction of the mention messages (fixed order -> deterministic)
+    row_store<D>(amt, s_acc + warp * D, lane);
+    if (FULL) row_store<D>(ami, s_acc + (NW + warp) * D, lane);
+    __syncthreads();
+    for (int i = tid; i < (FULL ? 2 : 1) * D; i += NW * 32) {
+      const int which = i / D, col = i - which * D;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += s_acc[(which * NW + w) * D + col];
+      const float zval = (which ? s_mi[col] : s_mt[col]) + t * invC;
+      bf16 h, l;
+      split_bf16(zval, h, l);
+      const long long zr = which ? B + b : b;
+      a.z_hi[zr * D + col] = h;
+      if (a.z_lo) a.z_lo[zr * D + col] = l;
+    }
+  }
+}
+
+template <int D, int NW>
+static int launch_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
+  const size_t smem = (size_t)(6 * D + 2 * NW * D) * sizeof(float);
+  const int grid = a.B < 148 * 8 ? a.B : 148 * 8;
+  if (a.full) {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_fwd_kernel<D, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    gcn_layer_fwd_kernel<D, NW, true><<<grid, NW * 32, smem, stream>>>(a);
+  } else {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_fwd_kernel<D, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    gcn_layer_fwd_kernel<D, NW, false><<<grid, NW * 32, smem, stream>>>(a);
+  }
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
+  if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: gcn_embed_dim %d not built (768 only)", a.D);
+  return a.C < 32 ? launch_layer_fwd<768, 4>(stream, a) : launch_layer_fwd<768, 8>(stream, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mention_ln: x = gelu(LN(h)) for `rows` rows (warp per row) -> fp32 and optional planes
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) mention_ln_kernel(const float* __restrict__ h, long long rows,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ x,
+                                                          bf16* __restrict__ x_hi, bf16* __restrict__ x_lo) {
+  __shared__ __align__(16) float s_gamma[D];
+  __shared__ __align__(16) float s_beta[D];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    s_gamma[i] = gamma[i];
+    s_beta[i] = beta[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    RowT<D> row;
+    row_load<D>(row, h + r * D, lane);
+    row_ln_gelu<D>(row, s_gamma, s_beta, lane);
+    if (x) row_store<D>(row, x + r * D, lane);
+    if (x_hi) row_store_planes<D>(row, x_hi + r * D, x_lo ? x_lo + r * D : nullptr, lane);
+  }
+}
+
+int mention_ln(cudaStream_t stream, int D, const float* h, long long rows, const float* gamma, const float* beta,
+               float* x, bf16* x_hi, bf16* x_lo) {
+  if (D != 768) return fail(DRIN_ERR_ARG, "mention_ln: gcn_embed_dim %d not built (768 only)", D);
+  const long long blocks = (rows + 7) / 8;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  mention_ln_kernel<768><<<grid, 256, 0, stream>>>(h, rows, gamma, beta, x, x_hi, x_lo);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rowdot: out[r] = x[r] . w   (beta_u = fu . b_v)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x, long long rows,
+                                                     const float* __restrict__ w, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    RowT<D> row;
+    row_load<D>(row, x + r * D, lane);
+    const float d = warp_sum(row_dot<D>(row, w, lane));
+    if (lane == 0) out[r] = d;
+  }
+}
+
+int rowdot(cudaStream_t stream, int D, const float* x, long long rows, const float* w, float* out) {
+  if (D != 768) return fail(DRIN_ERR_ARG, "rowdot: gcn_embed_dim %d not built (768 only)", D);
+  const long long blocks = (rows + 7) / 8;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  rowdot_kernel<768><<<grid, 256, 0, stream>>>(x, rows, w, out);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// score: scores[b, c] = cos(gelu(LN(h_mt[b])), gelu(LN(h_et[b, c])))   (model.py:207-209)
+// ---------------------------------------------------------------------------------------------
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32) score_kernel(const float* __restrict__ h_mt, const float* __restrict__ h_et,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int B, int C,
+                                                         float* __restrict__ scores) {
+  __shared__ __align__(16) float s_gamma[D];
+  __shared__ __align__(16) float s_beta[D];
+  __shared__ __align__(16) float s_m[D];
+  __shared__ float s_mnorm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += NW * 32) {
+    s_gamma[i] = gamma[i];
+    s_beta[i] = beta[i];
+  }
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    if (warp == 0) {
+      RowT<D> m;
+      row_load<D>(m, h_mt + (long long)b * D, lane);
+      row_ln_gelu<D>(m, s_gamma, s_beta, lane);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < RowT<D>::NV * 4; ++i) q += m.v[i] * m.v[i];
+      q = warp_sum(q);
+      row_store<D>(m, s_m, lane);
+      if (lane == 0) s_mnorm = fmaxf(sqrtf(q), 1e-8f);
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += NW) {
+      const long long r = (long long)b * C + c;
+      RowT<D> e;
+      row_load<D>(e, h_et + r * D, lane);
+      row_ln_gelu<D>(e, s_gamma, s_beta, lane);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < RowT<D>::NV * 4; ++i) q += e.v[i] * e.v[i];
+      q = warp_sum(q);
+      const float d = warp_sum(row_dot<D>(e, s_m, lane));
+      if (lane == 0) scores[r] = d / (s_mnorm * fmaxf(sqrtf(q), 1e-8f));
+    }
+  }
+}
+
+int score_fwd(cudaStream_t stream, int D, const float* h_mt, const float* h_et, const float* gamma, const float* beta,
+              int B, int C, float* scores) {
+  if (D != 768) return fail(DRIN_ERR_ARG, "score: gcn_embed_dim %d not built (768 only)", D);
+  const int grid = B < 148 * 8 ? B : 148 * 8;
+  if (C < 32) score_kernel<768, 4><<<grid, 128, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);
+  else score_kernel<768, 8><<<grid, 256, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+}  // namespace drin

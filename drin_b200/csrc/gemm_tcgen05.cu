@@ -1,0 +1,625 @@
+// tcgen05 / TMEM / TMA GEMM family for the DRIN projections and GCN updates (sm_100a only).
+//
+//   C[M,N] (+bias) = op(A) * op(B), bf16 operands, fp32 accumulation in TMEM.
+//
+// Two numeric modes share one kernel:
+//   * planes == 1  : plain bf16 operands, one tensor-core pass            ("bf16 mode")
+//   * planes == 2  : every fp32 operand is carried as two bf16 planes x = hi + lo; the kernel issues
+//                    hi*hi + hi*lo + lo*hi into the same TMEM accumulator ("split-bf16", fp32 parity:
+//                    per-product relative error <= 3 * 2^-18 ~ 1.1e-5).
+// Three layouts (gemm.cuh): NT (forward), NN (data gradient), TN (weight gradient, split-K).  The
+// transposed operands are fed MN-major straight from the row-major tensors -- no transposes in HBM.
+//
+// Structure: persistent CTAs (grid = min(tiles, #SM)), 128x256 output tile, BLOCK_K = 64,
+// warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 = epilogue
+// (tcgen05.ld -> bias -> global / split planes).  Two 256-column TMEM accumulators let the epilogue
+// of tile i overlap the MMAs of tile i+1.  All mbarrier waits carry a watchdog so a protocol bug traps
+// instead of hanging the GPU.
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm.cuh"
+
+namespace drin {
+
+static constexpr int BM = 128;
+static constexpr int BN = 256;
+static constexpr int BK = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
+static constexpr int UMMA_K = 16;
+static constexpr int A_PLANE_BYTES = BM * BK * 2;   // 16 KB
+static constexpr int B_PLANE_BYTES = BN * BK * 2;   // 32 KB
+static constexpr int ACC_STAGES = 2;
+static constexpr int TMEM_COLS = ACC_STAGES * BN;   // 512
+static constexpr int MAX_STAGES = 4;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int SMEM_TILE_BYTES = 192 * 1024;
+static constexpr int EPI_LD = 36;                                    // padded row (floats) of the epilogue transpose
+static constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_LD * 4;          // 4 epilogue warps x 32 rows
+static constexpr int SMEM_TOTAL_BYTES = SMEM_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+
+struct GemmKernelParams {
+  long long M;          // output rows
+  int N;                // output cols
+  int planes;           // 1 or 2
+  int stages;           // smem ring depth
+  int ksplit;           // number of contraction slices
+  int kblocks_total;    // ceil(K / BK)
+  int kblocks_per_split;
+  int m_tiles, n_tiles;
+  float* C;
+  long long c_split_stride;   // elements between split-K partials
+  int ldc;
+  const float* bias;
+  bf16* out_hi;
+  bf16* out_lo;
+  int ld_planes;
+  uint32_t mn_lbo, mn_sbo;    // MN-major descriptor strides (bytes)
+  int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait with a 4 s watchdog: a broken producer/consumer protocol traps (launch failure) instead of
+// hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      if (error_flag) atomicExch(error_flag, tag);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                    const GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B alignment
+  const uint32_t bar_base = smem_base + SMEM_TILE_BYTES;
+  // barrier block: full[4] empty[4] tmem_full[2] tmem_empty[2] (8 B each) + tmem base (4 B)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + ACC_STAGES + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 2 * ACC_STAGES);
+  const uint32_t stage_smem = bar_base + 256u;           // epilogue transpose staging (16-B aligned)
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stage_bytes = p.planes * (A_PLANE_BYTES + B_PLANE_BYTES);
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.planes == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);     // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int t, int& m_blk, int& n_blk, int& ks) {
+    const int per_split = p.m_tiles * p.n_tiles;
+    ks = t / per_split;
+    const int r = t - ks * per_split;
+    m_blk = r / p.n_tiles;
+    n_blk = r - m_blk * p.n_tiles;
+  };
+  auto kblock_range = [&](int ks, int& kb0, int& kb1) {
+    kb0 = ks * p.kblocks_per_split;
+    kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, ks, kb0, kb1;
+        tile_coords(t, m_blk, n_blk, ks);
+        kblock_range(ks, kb0, kb1);
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
+          const uint32_t fb = full_bar(stage);
+          mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
+          const uint32_t sA = smem_base + stage * stage_bytes;
+          const uint32_t sB = sA + p.planes * A_PLANE_BYTES;
+          const int k0 = kb * BK;
+          for (int pl = 0; pl < p.planes; ++pl) {
+            const CUtensorMap* ma = pl ? &tmA1 : &tmA0;
+            const CUtensorMap* mb = pl ? &tmB1 : &tmB0;
+            const uint32_t a_dst = sA + pl * A_PLANE_BYTES;
+            const uint32_t b_dst = sB + pl * B_PLANE_BYTES;
+            if (!A_MN) {
+              tma_load_2d(a_dst, ma, fb, k0, m0);                       // box {64 k, 128 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)                         // box {64 m, 64 k-rows}
+                tma_load_2d(a_dst + j * (BK * 128), ma, fb, m0 + 64 * j, k0);
+            }
+            if (!B_MN) {
+              tma_load_2d(b_dst, mb, fb, k0, n0);                       // box {64 k, 256 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(b_dst + j * (BK * 128), mb, fb, n0 + 64 * j, k0);
+            }
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accum, bf16 x bf16
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = A_MN ? p.mn_lbo : 16u, a_sbo = A_MN ? p.mn_sbo : 1024u;
+      const uint32_t b_lbo = B_MN ? p.mn_lbo : 16u, b_sbo = B_MN ? p.mn_sbo : 1024u;
+      const uint32_t a_kstep = A_MN ? UMMA_K * 128u : UMMA_K * 2u;      // bytes per UMMA_K step
+      const uint32_t b_kstep = B_MN ? UMMA_K * 128u : UMMA_K * 2u;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, ks, kb0, kb1;
+        tile_coords(t, m_blk, n_blk, ks);
+        kblock_range(ks, kb0, kb1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.error_flag, 2);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.error_flag, 3);
+          tcgen05_fence_after();
+          const uint32_t sA = smem_base + stage * stage_bytes;
+          const uint32_t sB = sA + p.planes * A_PLANE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a0 = make_smem_desc(sA + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t b0 = make_smem_desc(sB + k * b_kstep, b_lbo, b_sbo);
+            umma_bf16(d_tmem, a0, b0, idesc, accumulate);
+            accumulate = 1;
+            if (p.planes == 2) {
+              const uint64_t a1 = make_smem_desc(sA + A_PLANE_BYTES + k * a_kstep, a_lbo, a_sbo);
+              const uint64_t b1 = make_smem_desc(sB + B_PLANE_BYTES + k * b_kstep, b_lbo, b_sbo);
+              umma_bf16(d_tmem, a0, b1, idesc, 1u);     // hi * lo
+              umma_bf16(d_tmem, a1, b0, idesc, 1u);     // lo * hi
+            }
+          }
+          umma_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (kb1 <= kb0) umma_commit(tfull_bar(acc));     // empty slice (cannot happen; keeps protocol live)
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps) ==========================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m_blk, n_blk, ks;
+      tile_coords(t, m_blk, n_blk, ks);
+      mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, 4);
+      tcgen05_fence_after();
+      // Each thread owns one accumulator row in TMEM (32x32b shape); a padded smem transpose turns
+      // that into row-contiguous 128-B global stores (4 rows x 128 B per warp instruction).
+      const long long row_base = (long long)m_blk * BM + q * 32;
+      float* stg = reinterpret_cast<float*>(smem_raw + (stage_smem - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
+      const int sub = lane >> 3, l8 = lane & 7;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + chunk * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + chunk * 32;
+        if (col0 >= p.N) continue;                       // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(stg + lane * EPI_LD + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncwarp();
+        const int col = col0 + 4 * l8;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (col + 3 < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          else {
+            if (col < p.N) bv.x = __ldg(p.bias + col);
+            if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
+            if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + sub;
+          const long long row = row_base + r;
+          float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * l8);
+          f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+          if (row < p.M && col < p.N) {
+            if (col + 3 < p.N) {
+              if (p.C) *reinterpret_cast<float4*>(p.C + (long long)ks * p.c_split_stride + row * p.ldc + col) = f;
+              if (p.out_hi) {
+                bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+                split_bf16(f.x, h0, l0); split_bf16(f.y, h1, l1); split_bf16(f.z, h2, l2); split_bf16(f.w, h3, l3);
+                *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_planes + col) =
+                    make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+                if (p.out_lo)
+                  *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_planes + col) =
+                      make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+              }
+            } else {
+              const float ff[4] = {f.x, f.y, f.z, f.w};
+              for (int j = 0; j < 4 && col + j < p.N; ++j) {
+                if (p.C) p.C[(long long)ks * p.c_split_stride + row * p.ldc + col + j] = ff[j];
+                if (p.out_hi) {
+                  bf16 h, l;
+                  split_bf16(ff[j], h, l);
+                  p.out_hi[row * p.ld_planes + col + j] = h;
+                  if (p.out_lo) p.out_lo[row * p.ld_planes + col + j] = l;
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// deterministic split-K reduction: C[i] = bias + sum_s partial[s][i]
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long split_stride,
+                                     float* __restrict__ C, long long M, int N, int ldc,
+                                     const float* __restrict__ bias) {
+  const long long total4 = M * (long long)(N / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (N / 4);
+    const int c = (int)(i - r * (N / 4)) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) acc = *reinterpret_cast<const float4*>(bias + c);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + s * split_stride + r * ldc + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(C + r * ldc + c) = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr; long long rows; int cols, ld, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ std::hash<long long>()(k.rows);
+    h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+
+// bf16 row-major [rows, cols] (leading dim ld) -> 2-D map with box {64 cols, box_rows}, SWIZZLE_128B
+static int make_tmap(const bf16* ptr, long long rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  if (((uintptr_t)ptr & 15) || (ld % 8) != 0)
+    return fail(DRIN_ERR_ARG, "GEMM operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%d)", ptr, ld);
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) {
+    *out = it->second;
+    return DRIN_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(DRIN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DRIN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d ld=%d box_rows=%d", (int)r, rows,
+                cols, ld, box_rows);
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return DRIN_OK;
+}
+
+static int g_mn_lbo = 0, g_mn_sbo = 0;
+void gemm_debug_set_mn_desc(int lbo_bytes, int sbo_bytes) {
+  g_mn_lbo = lbo_bytes;
+  g_mn_sbo = sbo_bytes;
+}
+
+static int g_num_sms = 0;
+static int* g_error_flag = nullptr;
+
+static int gemm_init_once() {
+  static int status = -1;
+  if (status >= 0) return status;
+  int dev = 0;
+  DRIN_CUDA(cudaGetDevice(&dev));
+  DRIN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_TOTAL_BYTES));
+  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_TOTAL_BYTES));
+  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_TOTAL_BYTES));
+  DRIN_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
+  DRIN_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  status = DRIN_OK;
+  return status;
+}
+
+int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M, int N,
+                 long long K, const GemmEpilogue& ep, int ksplit, float* partial) {
+  DRIN_TRY(gemm_init_once());
+  if (M <= 0 || N <= 0 || K <= 0) return fail(DRIN_ERR_ARG, "gemm: empty problem M=%lld N=%d K=%lld", M, N, K);
+  const int planes = A.lo ? 2 : 1;
+  if ((A.lo != nullptr) != (B.lo != nullptr)) return fail(DRIN_ERR_ARG, "gemm: A and B must have the same planes");
+  if (!ep.C && !ep.out_hi) return fail(DRIN_ERR_ARG, "gemm: no output requested");
+  if (ep.C && (ep.ldc % 4)) return fail(DRIN_ERR_ARG, "gemm: ldc must be a multiple of 4");
+  if (ep.out_hi && (ep.ld_planes % 8)) return fail(DRIN_ERR_ARG, "gemm: ld_planes must be a multiple of 8");
+  const bool a_mn = layout == GEMM_TN, b_mn = layout != GEMM_NT;
+  // operand shape checks
+  const long long a_rows = a_mn ? K : M;
+  const long long a_cols = a_mn ? M : K;
+  const long long b_rows = b_mn ? K : N;
+  const long long b_cols = b_mn ? N : K;
+  if (A.rows != a_rows || A.cols != a_cols || B.rows != b_rows || B.cols != b_cols)
+    return fail(DRIN_ERR_ARG, "gemm: operand shapes do not match layout %d (A %lldx%d, B %lldx%d, M=%lld N=%d K=%lld)",
+                (int)layout, A.rows, A.cols, B.rows, B.cols, M, N, K);
+
+  CUtensorMap tA0, tA1, tB0, tB1;
+  const int a_box = a_mn ? BK : BM, b_box = b_mn ? BK : BN;
+  DRIN_TRY(make_tmap(A.hi, A.rows, A.cols, A.ld, a_box, &tA0));
+  DRIN_TRY(make_tmap(B.hi, B.rows, B.cols, B.ld, b_box, &tB0));
+  if (planes == 2) {
+    DRIN_TRY(make_tmap(A.lo, A.rows, A.cols, A.ld, a_box, &tA1));
+    DRIN_TRY(make_tmap(B.lo, B.rows, B.cols, B.ld, b_box, &tB1));
+  } else {
+    tA1 = tA0;
+    tB1 = tB0;
+  }
+
+  GemmKernelParams p{};
+  p.M = M;
+  p.N = N;
+  p.planes = planes;
+  p.stages = planes == 2 ? 2 : 4;
+  p.kblocks_total = (int)((K + BK - 1) / BK);
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > p.kblocks_total) ksplit = p.kblocks_total;
+  p.kblocks_per_split = (p.kblocks_total + ksplit - 1) / ksplit;
+  ksplit = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;   // no empty slices
+  p.ksplit = ksplit;
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.n_tiles = (N + BN - 1) / BN;
+  p.bias = ksplit > 1 ? nullptr : ep.bias;
+  p.ldc = ep.ldc;
+  p.out_hi = ep.out_hi;
+  p.out_lo = ep.out_lo;
+  p.ld_planes = ep.ld_planes;
+  p.mn_lbo = g_mn_lbo ? (uint32_t)g_mn_lbo : (uint32_t)(BK * 128);
+  p.mn_sbo = g_mn_sbo ? (uint32_t)g_mn_sbo : 1024u;
+  p.error_flag = g_error_flag;
+  if (ksplit > 1) {
+    if (!partial || !ep.C || ep.out_hi || (N % 4))
+      return fail(DRIN_ERR_ARG, "gemm: split-K needs a partial buffer, an fp32 output with N %% 4 == 0 and no planes");
+    p.C = partial;
+    p.c_split_stride = M * (long long)ep.ldc;
+  } else {
+    p.C = ep.C;
+    p.c_split_stride = 0;
+  }
+  const long long tiles = (long long)p.m_tiles * p.n_tiles * ksplit;
+  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  if (layout == GEMM_NT)
+    gemm_tcgen05_kernel<false, false><<<grid, GEMM_THREADS, SMEM_TOTAL_BYTES, stream>>>(tA0, tA1, tB0, tB1, p);
+  else if (layout == GEMM_NN)
+    gemm_tcgen05_kernel<false, true><<<grid, GEMM_THREADS, SMEM_TOTAL_BYTES, stream>>>(tA0, tA1, tB0, tB1, p);
+  else
+    gemm_tcgen05_kernel<true, true><<<grid, GEMM_THREADS, SMEM_TOTAL_BYTES, stream>>>(tA0, tA1, tB0, tB1, p);
+  DRIN_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    const long long total4 = M * (long long)(N / 4);
+    const int rgrid = (int)((total4 + 255) / 256 < 4 * g_num_sms ? (total4 + 255) / 256 : 4 * g_num_sms);
+    splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(partial, ksplit, p.c_split_stride, ep.C, M, N, ep.ldc, ep.bias);
+    DRIN_LAUNCH_CHECK();
+  }
+  return DRIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core fp32 reference (tests / bring-up only)
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_reference_kernel(int layout, const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, int lda,
+                                      const bf16* __restrict__ b_hi, const bf16* __restrict__ b_lo, int ldb,
+                                      long long M, int N, long long K, float* __restrict__ C, int ldc,
+                                      const float* __restrict__ bias, bf16* out_hi, bf16* out_lo, int ldp) {
+  const long long m = blockIdx.y * (long long)blockDim.y + threadIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M || n >= N) return;
+  float acc = 0.f;
+  for (long long k = 0; k < K; ++k) {
+    const long long ai = layout == GEMM_TN ? k * lda + m : m * lda + k;
+    const long long bi = layout == GEMM_NT ? (long long)n * ldb + k : k * ldb + n;
+    float a = __bfloat162float(a_hi[ai]);
+    float b = __bfloat162float(b_hi[bi]);
+    if (a_lo) a += __bfloat162float(a_lo[ai]);
+    if (b_lo) b += __bfloat162float(b_lo[bi]);
+    acc = fmaf(a, b, acc);
+  }
+  if (bias) acc += bias[n];
+  if (C) C[m * ldc + n] = acc;
+  if (out_hi) {
+    bf16 h, l;
+    split_bf16(acc, h, l);
+    out_hi[m * ldp + n] = h;
+    if (out_lo) out_lo[m * ldp + n] = l;
+  }
+}
+
+int gemm_reference_simt(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M,
+                        int N, long long K, const GemmEpilogue& ep) {
+  dim3 block(32, 8);
+  dim3 grid((N + 31) / 32, (unsigned)((M + 7) / 8));
+  gemm_reference_kernel<<<grid, block, 0, stream>>>((int)layout, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, M, N, K, ep.C,
+                                                    ep.ldc, ep.bias, ep.out_hi, ep.out_lo, ep.ld_planes);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+}  // namespace drin

@@ -1,0 +1,145 @@
+// Warp-per-row register tiles for the 768-wide vertex rows (shared by the forward and backward GCN kernels).
+// Lane l of a warp holds elements (j*32 + l)*4 .. +3 for j < D/128: every global access is a coalesced
+// 512-B warp transaction and every shared-memory access a conflict-free 128-bit one.
+#pragma once
+#include "common.cuh"
+
+namespace drin {
+
+template <int D>
+struct RowT {
+  static constexpr int NV = D / 128;      // float4 per lane
+  float v[NV * 4];
+};
+
+template <int D>
+__device__ __forceinline__ void row_load(RowT<D>& r, const float* __restrict__ p, int lane) {
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(p + (j * 32 + lane) * 4);
+    r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
+  }
+}
+template <int D>
+__device__ __forceinline__ void row_store(const RowT<D>& r, float* __restrict__ p, int lane) {
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j)
+    *reinterpret_cast<float4*>(p + (j * 32 + lane) * 4) =
+        make_float4(r.v[4 * j], r.v[4 * j + 1], r.v[4 * j + 2], r.v[4 * j + 3]);
+}
+template <int D>
+__device__ __forceinline__ void row_store_planes(const RowT<D>& r, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                 int lane) {
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+    split_bf16(r.v[4 * j], h0, l0);
+    split_bf16(r.v[4 * j + 1], h1, l1);
+    split_bf16(r.v[4 * j + 2], h2, l2);
+    split_bf16(r.v[4 * j + 3], h3, l3);
+    *reinterpret_cast<uint2*>(hi + (j * 32 + lane) * 4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    if (lo) *reinterpret_cast<uint2*>(lo + (j * 32 + lane) * 4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+  }
+}
+template <int D>
+__device__ __forceinline__ float row_dot(const RowT<D>& a, const float* __restrict__ s, int lane) {
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(s + (j * 32 + lane) * 4);
+    acc += a.v[4 * j] * t.x + a.v[4 * j + 1] * t.y + a.v[4 * j + 2] * t.z + a.v[4 * j + 3] * t.w;
+  }
+  return acc;
+}
+
+// y = gelu(LayerNorm(h)) in place (eps 1e-5, biased variance, like nn.LayerNorm); gamma/beta in smem
+template <int D>
+__device__ __forceinline__ void row_ln_gelu(RowT<D>& r, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) s += r.v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) {
+    const float d = r.v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
+    const float4 b = *reinterpret_cast<const float4*>(beta + (j * 32 + lane) * 4);
+    r.v[4 * j] = gelu_f((r.v[4 * j] - mean) * rstd * g.x + b.x);
+    r.v[4 * j + 1] = gelu_f((r.v[4 * j + 1] - mean) * rstd * g.y + b.y);
+    r.v[4 * j + 2] = gelu_f((r.v[4 * j + 2] - mean) * rstd * g.z + b.z);
+    r.v[4 * j + 3] = gelu_f((r.v[4 * j + 3] - mean) * rstd * g.w + b.w);
+  }
+}
+
+
+// acc[slice] += r  (per-warp shared-memory accumulator slice, no conflicts, no atomics)
+template <int D>
+__device__ __forceinline__ void row_accum_smem(const RowT<D>& r, float* __restrict__ s, int lane) {
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    float4* p = reinterpret_cast<float4*>(s + (j * 32 + lane) * 4);
+    float4 t = *p;
+    t.x += r.v[4 * j]; t.y += r.v[4 * j + 1]; t.z += r.v[4 * j + 2]; t.w += r.v[4 * j + 3];
+    *p = t;
+  }
+}
+
+// Backward of a = gelu(LayerNorm(h)): on entry `d` holds dL/da, on exit dL/dh.
+// Accumulates dL/dgamma, dL/dbeta into the per-warp slices pg, pb.
+template <int D>
+__device__ __forceinline__ void row_ln_gelu_bwd(const RowT<D>& h, RowT<D>& d, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float* __restrict__ pg,
+                                                float* __restrict__ pb, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) s += h.v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) {
+    const float t = h.v[i] - mean;
+    q += t * t;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + off);
+    const float4 b = *reinterpret_cast<const float4*>(beta + off);
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+    float4 ag = *reinterpret_cast<float4*>(pg + off);
+    float4 ab = *reinterpret_cast<float4*>(pb + off);
+    float* agp = reinterpret_cast<float*>(&ag);
+    float* abp = reinterpret_cast<float*>(&ab);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (h.v[4 * j + k] - mean) * rstd;
+      const float dy = d.v[4 * j + k] * gelu_grad_f(xh * gg[k] + bb[k]);
+      agp[k] += dy * xh;
+      abp[k] += dy;
+      const float dxh = dy * gg[k];
+      d.v[4 * j + k] = dxh;
+      m1 += dxh;
+      m2 += dxh * xh;
+    }
+    *reinterpret_cast<float4*>(pg + off) = ag;
+    *reinterpret_cast<float4*>(pb + off) = ab;
+  }
+  m1 = warp_sum(m1) * (1.0f / D);
+  m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) {
+    const float xh = (h.v[i] - mean) * rstd;
+    d.v[i] = rstd * (d.v[i] - m1 - xh * m2);
+  }
+}
+
+}  // namespace drin

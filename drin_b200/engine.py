@@ -1,0 +1,272 @@
+"""Host-side driver of the CUDA hot path: turns the reference's 14-tensor batch and state_dict-named
+parameters into the plain-pointer structs of the C ABI (include/drin_b200.h) and owns the workspace.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in libdrin_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+FP32, BF16 = 0, 1
+
+INPUT_NAMES = (
+    "mention_text_feature", "mention_text_mask", "mention_start_pos", "mention_end_pos",
+    "mention_image_feature", "mention_object_feature", "mention_object_score", "entity_text_feature",
+    "entity_text_mask", "entity_image_feature", "entity_object_feature", "entity_object_score",
+    "miet_similarity", "mtei_similarity",
+)
+
+# state_dict keys (reference drin/model.py:21-24,111-119,159-162) -> fields of drin_params
+VERTEX_KEYS = (
+    ("vertex_encoder.mention_text_encoder.final_layer.linear.weight", "w_mt"),
+    ("vertex_encoder.mention_text_encoder.final_layer.linear.bias", "b_mt"),
+    ("vertex_encoder.entity_text_encoder.final_layer.weight", "w_et"),
+    ("vertex_encoder.entity_text_encoder.final_layer.bias", "b_et"),
+    ("vertex_encoder.mention_image_linear.weight", "w_mi"),
+    ("vertex_encoder.mention_image_linear.bias", "b_mi"),
+    ("vertex_encoder.entity_image_linear.weight", "w_ei"),
+    ("vertex_encoder.entity_image_linear.bias", "b_ei"),
+)
+LAYER_FIELDS = (
+    ("w_h.weight", "w_h"), ("w_h.bias", "b_h"), ("w_u.weight", "w_u"), ("w_u.bias", "b_u"),
+    ("w_v.weight", "w_v"), ("w_v.bias", "b_v"), ("layer_norm.weight", "ln_w"), ("layer_norm.bias", "ln_b"),
+)
+
+
+def param_keys(num_layers: int) -> List[str]:
+    keys = [k for k, _ in VERTEX_KEYS]
+    for l in range(num_layers):
+        keys += [f"gcn_layers.{l}.{s}" for s, _ in LAYER_FIELDS]
+    return keys
+
+
+def param_shapes(num_layers: int, D: int = 768, R: int = 2048) -> Dict[str, Tuple[int, ...]]:
+    shapes = {
+        VERTEX_KEYS[0][0]: (D, D), VERTEX_KEYS[1][0]: (D,), VERTEX_KEYS[2][0]: (D, D), VERTEX_KEYS[3][0]: (D,),
+        VERTEX_KEYS[4][0]: (D, R), VERTEX_KEYS[5][0]: (D,), VERTEX_KEYS[6][0]: (D, R), VERTEX_KEYS[7][0]: (D,),
+    }
+    for l in range(num_layers):
+        for s, _ in LAYER_FIELDS:
+            shapes[f"gcn_layers.{l}.{s}"] = (D, D) if s in ("w_h.weight", "w_u.weight", "w_v.weight") else (D,)
+    return shapes
+
+
+def dead_param_keys(num_layers: int) -> List[str]:
+    """Parameters that never receive a gradient in the reference (grad is None): the edge update of the
+    last GCN layer is dead code (drin/model.py:131-134)."""
+    l = num_layers - 1
+    return [f"gcn_layers.{l}.{s}" for s in ("w_u.weight", "w_u.bias", "w_v.weight", "w_v.bias")]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class Problem:
+    """Shapes of one call, derived from the batch exactly like the reference switches on tensor rank
+    (drin/model.py:43-44,73-75,78-83)."""
+    B: int
+    C: int
+    Lm: int
+    Le: int          # 0 = WikiDiverse layout
+    P: int
+    Om: int
+    Oe: int
+    D: int
+    R: int
+    precision: int
+
+    def key(self):
+        return (self.B, self.C, self.Lm, self.Le, self.P, self.Om, self.Oe, self.D, self.R, self.precision)
+
+
+def inspect_batch(batch: Sequence[torch.Tensor], num_candidates_model: Optional[int] = None) -> Problem:
+    if len(batch) != 14:
+        raise ValueError(f"DRIN forward expects a 14-tensor batch (drin/model.py:164-180), got {len(batch)}")
+    (mtf, _mm, start, end, mif, mof, mos, etf, emask, eif, eof, eos, miet, mtei) = batch
+    for name, t in zip(INPUT_NAMES, batch):
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor (no CPU fallback in drin_b200)")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous")
+    feat_dtype = mtf.dtype
+    if feat_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"feature dtype {feat_dtype} not supported (float32 or bfloat16)")
+    for name, t in (("mention_image_feature", mif), ("mention_object_feature", mof), ("entity_text_feature", etf),
+                    ("entity_image_feature", eif), ("entity_object_feature", eof)):
+        if t.dtype != feat_dtype:
+            raise RuntimeError(f"{name} has dtype {t.dtype}, expected {feat_dtype} like mention_text_feature")
+    for name, t in (("mention_object_score", mos), ("entity_object_score", eos), ("miet_similarity", miet),
+                    ("mtei_similarity", mtei)):
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    for name, t in (("mention_start_pos", start), ("mention_end_pos", end)):
+        if t.dtype != torch.int64:
+            raise RuntimeError(f"{name} must be int64, got {t.dtype}")
+    if mtf.dim() != 3:
+        raise RuntimeError(f"mention_text_feature must be [B, Lm, D], got {tuple(mtf.shape)}")
+    B, Lm, D = mtf.shape
+    if etf.dim() == 3:
+        Le = 0
+    elif etf.dim() == 4:
+        Le = etf.shape[2]
+        if emask.dtype != torch.int64 or tuple(emask.shape) != (B, etf.shape[1], Le):
+            raise RuntimeError(f"entity_text_mask must be int64 [B, C, Le], got {emask.dtype} {tuple(emask.shape)}")
+    else:
+        raise RuntimeError(f"entity_text_feature must have rank 3 or 4, got {tuple(etf.shape)}")
+    Cc = etf.shape[1]
+    if num_candidates_model is not None and Cc != num_candidates_model:
+        # the reference hard-codes num_candidates_model in its expand() calls (model.py:72,80-85,146,150,208)
+        raise RuntimeError(f"batch has {Cc} candidate slots but num_candidates_model = {num_candidates_model}")
+    if mif.dim() != 3 or mif.shape[0] != B:
+        raise RuntimeError(f"mention_image_feature must be [B, P, R], got {tuple(mif.shape)}")
+    P, R = mif.shape[1], mif.shape[2]
+    if mof.dim() == 4:
+        if mof.shape[2] != 1:
+            raise RuntimeError("mention_object_feature: only a singleton crop dim is supported ([B, Om, 1, R])")
+        Om = mof.shape[1]
+    elif mof.dim() == 3:
+        Om = mof.shape[1]
+    else:
+        raise RuntimeError(f"mention_object_feature has bad shape {tuple(mof.shape)}")
+    if eof.dim() == 5:
+        if eof.shape[3] != 1:
+            raise RuntimeError("entity_object_feature: only a singleton crop dim is supported ([B, C, Oe, 1, R])")
+        Oe = eof.shape[2]
+    elif eof.dim() == 4:
+        Oe = eof.shape[2]
+    else:
+        raise RuntimeError(f"entity_object_feature has bad shape {tuple(eof.shape)}")
+    if eif.dim() == 4 and eif.shape[2] != 1:
+        raise RuntimeError("entity_image_feature: only [B, C, R] or [B, C, 1, R] is supported")
+
+    def want(name, t, shape):
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+
+    want("mention_start_pos", start, (B,))
+    want("mention_end_pos", end, (B,))
+    want("mention_object_score", mos, (B, Om))
+    want("entity_object_score", eos, (B, Cc, Oe))
+    want("miet_similarity", miet, (B, Cc))
+    want("mtei_similarity", mtei, (B, Cc))
+    if eif.numel() != B * Cc * R or eof.numel() != B * Cc * Oe * R or mof.numel() != B * Om * R:
+        raise RuntimeError("image / object feature shapes are inconsistent with [B, C, R]")
+    if etf.shape[0] != B or etf.shape[-1] != D:
+        raise RuntimeError(f"entity_text_feature has bad shape {tuple(etf.shape)}")
+    return Problem(B, Cc, Lm, Le, P, Om, Oe, D, R, BF16 if feat_dtype == torch.bfloat16 else FP32)
+
+
+class Engine:
+    """One instance per module: caches the workspace and marshals calls into the C ABI."""
+
+    def __init__(self, num_layers: int, edge_enabled: Sequence[float] = (1, 1, 1, 1)):
+        self.lib = _lib.load()
+        self.num_layers = int(num_layers)
+        self.edge_enabled = tuple(float(x) for x in edge_enabled)
+        if len(self.edge_enabled) != 4:
+            raise ValueError("gcn_edge_enabled must have 4 entries")
+        self._ws: Optional[torch.Tensor] = None
+
+    # ---- struct marshalling -----------------------------------------------------------------
+    def config(self, pb: Problem, training: bool) -> _lib.DrinConfig:
+        cfg = _lib.DrinConfig()
+        cfg.batch, cfg.candidates, cfg.mention_tokens, cfg.entity_tokens = pb.B, pb.C, pb.Lm, pb.Le
+        cfg.regions, cfg.mention_objects, cfg.entity_objects = pb.P, pb.Om, pb.Oe
+        cfg.embed_dim, cfg.resnet_dim, cfg.gcn_layers = pb.D, pb.R, self.num_layers
+        cfg.precision, cfg.training = pb.precision, int(training)
+        for i in range(4):
+            cfg.edge_enabled[i] = self.edge_enabled[i]
+        return cfg
+
+    @staticmethod
+    def inputs(batch: Sequence[torch.Tensor]) -> _lib.DrinInputs:
+        s = _lib.DrinInputs()
+        for name, t in zip(INPUT_NAMES, batch):
+            setattr(s, name, t.data_ptr())
+        return s
+
+    def params(self, tensors: Dict[str, torch.Tensor], D: int, R: int) -> _lib.DrinParams:
+        """tensors: state_dict-keyed fp32 CUDA tensors (parameters, or gradient buffers of the same shapes)."""
+        s = _lib.DrinParams()
+        shapes = param_shapes(self.num_layers, D, R)
+        for key, fld in VERTEX_KEYS:
+            setattr(s, fld, self._checked(tensors, key, shapes[key]))
+        for l in range(self.num_layers):
+            for suffix, fld in LAYER_FIELDS:
+                key = f"gcn_layers.{l}.{suffix}"
+                setattr(s.layer[l], fld, self._checked(tensors, key, shapes[key]))
+        return s
+
+    @staticmethod
+    def _checked(tensors, key, shape) -> int:
+        t = tensors.get(key)
+        if t is None:
+            return 0
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"parameter {key}: need contiguous CUDA float32 {shape}, got {t.dtype} {tuple(t.shape)}")
+        if t.data_ptr() % 16:
+            raise RuntimeError(f"parameter {key} is not 16-byte aligned")
+        return t.data_ptr()
+
+    # ---- workspace --------------------------------------------------------------------------
+    def workspace_bytes(self, cfg) -> int:
+        n = C.c_size_t(0)
+        _lib.check(self.lib.drin_workspace_bytes(C.byref(cfg), C.byref(n)), "drin_workspace_bytes")
+        return n.value
+
+    def workspace(self, cfg, device) -> torch.Tensor:
+        need = self.workspace_bytes(cfg)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    # ---- calls ------------------------------------------------------------------------------
+    def forward(self, batch, params: Dict[str, torch.Tensor], training: bool,
+                num_candidates_model: Optional[int] = None):
+        pb = inspect_batch(batch, num_candidates_model)
+        cfg = self.config(pb, training)
+        dev = batch[0].device
+        with torch.cuda.device(dev):
+            ws = self.workspace(cfg, dev)
+            scores = torch.empty(pb.B, pb.C, dtype=torch.float32, device=dev)
+            ins = self.inputs(batch)
+            ps = self.params(params, pb.D, pb.R)
+            _lib.check(self.lib.drin_forward(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
+                                             C.c_size_t(ws.numel()), _ptr(scores), _stream()), "drin_forward")
+        return scores, (pb, cfg, ws)
+
+    def backward(self, ctx, batch, params, dscores: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+        pb, cfg, ws = ctx
+        if ws is not self._ws:
+            raise RuntimeError("workspace was re-planned between forward and backward")
+        dscores = dscores.contiguous()
+        with torch.cuda.device(dscores.device):
+            ins = self.inputs(batch)
+            ps = self.params(params, pb.D, pb.R)
+            gs = self.params(grads, pb.D, pb.R)
+            _lib.check(self.lib.drin_backward(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
+                                              C.c_size_t(ws.numel()), _ptr(dscores), C.byref(gs), _stream()),
+                       "drin_backward")
+
+    def debug_buffer(self, ctx, name: str, layer: int = 0) -> torch.Tensor:
+        """Copy of a named fp32 intermediate of the last forward (tests only)."""
+        pb, cfg, ws = ctx
+        ptr, rows, cols = C.c_void_p(0), C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.drin_debug_buffer(C.byref(cfg), _ptr(ws), name.encode(), C.c_int32(layer), C.byref(ptr),
+                                              C.byref(rows), C.byref(cols)), "drin_debug_buffer")
+        off = ptr.value - ws.data_ptr()
+        n = rows.value * cols.value
+        return ws[off:off + 4 * n].view(torch.float32).view(rows.value, cols.value).clone()
