@@ -48,6 +48,35 @@ int drin_forward(const drin_config* cfg, const drin_inputs* in, const drin_param
   return forward(*cfg, *in, *params, workspace, workspace_bytes, scores, (cudaStream_t)stream);
 }
 
+int drin_backward(const drin_config* cfg, const drin_inputs* in, const drin_params* params, void* workspace,
+                  size_t workspace_bytes, const float* dscores, const drin_params* grads, void* stream) {
+  if (!cfg || !in || !params || !grads) return fail(DRIN_ERR_ARG, "drin_backward: null argument");
+  return backward(*cfg, *in, *params, workspace, workspace_bytes, dscores, *grads, (cudaStream_t)stream);
+}
+
+int drin_loss_scratch_bytes(int32_t batch_global, int32_t candidates, size_t* bytes) {
+  if (!bytes || batch_global <= 0) return fail(DRIN_ERR_ARG, "drin_loss_scratch_bytes: bad argument");
+  *bytes = triplet_scratch_bytes(batch_global, candidates);
+  return DRIN_OK;
+}
+
+int drin_triplet_loss(const float* scores_all, const uint8_t* labels_all, int32_t batch_global, int32_t candidates,
+                      int32_t row_offset, int32_t rows_local, float margin, float* loss, float* dscores, void* scratch,
+                      void* stream) {
+  return triplet_loss((cudaStream_t)stream, scores_all, labels_all, batch_global, candidates, row_offset, rows_local,
+                      margin, loss, dscores, scratch);
+}
+
+int drin_topk_hits(const float* scores, const uint8_t* labels, int32_t batch, int32_t candidates, const int32_t* topk,
+                   int32_t n_k, int64_t* hits, void* stream) {
+  return topk_hits((cudaStream_t)stream, scores, labels, batch, candidates, topk, n_k, (long long*)hits);
+}
+
+int drin_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* skip_mask,
+                   int64_t n, int32_t step, float lr, float beta1, float beta2, float eps, void* stream) {
+  return adam_step((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, skip_mask, n, step, lr, beta1, beta2, eps);
+}
+
 int drin_frontend(const drin_config* cfg, const drin_inputs* in, float* span, float* mimean, float* epool,
                   float* edges, void* stream) {
   if (!cfg || !in) return fail(DRIN_ERR_ARG, "drin_frontend: null argument");

@@ -103,7 +103,7 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
     ws.dx0 = m.planes(rows * D, split);
     // split-K: enough slices to fill the machine for the [D, D] weight gradients (18 tiles each)
     ws.ksplit = 8;
-    ws.partial = m.take<float>((size_t)ws.ksplit * D * (R > D ? R : D));
+    ws.partial = m.take<float>((size_t)ws.ksplit * D * D > (size_t)3 * D * R ? (size_t)ws.ksplit * D * D : (size_t)3 * D * R);
     ws.colsum_ctas = 148 * 2;
     ws.colsum = m.take<float>((size_t)2 * ws.colsum_ctas * 3 * D);
   }

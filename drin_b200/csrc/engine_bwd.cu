@@ -1,0 +1,143 @@
+// Backward orchestration of the DRIN hot path (what loss.backward() does after reference train.py:34).
+// Mirrors engine.cu: per layer one data-gradient GEMM (dZ = dH W_h), one split-K weight-gradient GEMM
+// (dW_h = dH^T Z) and the fused memory-bound kernels of gcn_bwd.cu; the small mention-side GEMMs carry
+// the W_u / W_v gradients of the dynamic edge update.
+#include "engine.cuh"
+
+namespace drin {
+
+static Operand op(const Planes& p, long long rows, int cols, long long row_offset = 0) {
+  Operand o;
+  o.hi = p.hi + row_offset * cols;
+  o.lo = p.lo ? p.lo + row_offset * cols : nullptr;
+  o.rows = rows;
+  o.cols = cols;
+  o.ld = cols;
+  return o;
+}
+
+// C[M,N] = A[K,M]^T B[K,N], contraction split so that tiles * slices ~ one wave
+static int weight_grad(cudaStream_t s, const Workspace& ws, const Operand& A, const Operand& B, int M, int N, long long K,
+                       float* out) {
+  if (!out) return fail(DRIN_ERR_ARG, "gradient buffer is null");
+  GemmEpilogue ep;
+  ep.C = out;
+  ep.ldc = N;
+  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
+  int ksplit = 148 / tiles;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > ws.ksplit) ksplit = ws.ksplit;
+  return gemm_tcgen05(s, GEMM_TN, A, B, M, N, K, ep, ksplit, ws.partial);
+}
+
+int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,
+             size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream) {
+  if (!c.training) return fail(DRIN_ERR_ARG, "drin_backward needs a config with training = 1");
+  Workspace ws;
+  DRIN_TRY(plan_workspace(c, &in, workspace, ws));
+  if (!workspace || workspace_bytes < ws.bytes)
+    return fail(DRIN_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
+  if (!dscores) return fail(DRIN_ERR_ARG, "dscores is null");
+  if (ws.colsum_ctas != backward_ctas()) return fail(DRIN_ERR_ARG, "internal: partial-sum grid mismatch");
+  const long long B = c.batch, C = c.candidates, BC = B * C;
+  const int D = c.embed_dim, R = c.resnet_dim, L = c.gcn_layers;
+  float* partA = ws.colsum;
+  float* partB = ws.colsum + (size_t)ws.colsum_ctas * 3 * D;
+  float* dedges[2] = {ws.dedges, ws.dedges + 4 * BC};
+
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerWs& lw = ws.layer[l];
+    const drin_layer_params& lp = p.layer[l];
+    const drin_layer_params& lg = grads.layer[l];
+    if (l == L - 1) {
+      ScoreBwdArgs sa{};
+      sa.B = c.batch; sa.C = c.candidates; sa.D = D;
+      sa.h_mt = lw.h; sa.h_et = lw.h + B * D; sa.gamma = lp.ln_w; sa.beta = lp.ln_b; sa.dscores = dscores;
+      sa.dh_hi = ws.dh.hi; sa.dh_lo = ws.dh.lo; sa.partials = partA;
+      DRIN_TRY(score_bwd(stream, sa));
+      DRIN_TRY(colsum_reduce(stream, partA, nullptr, 3, D, lg.ln_w, lg.ln_b, lg.b_h));
+    }
+    // dZ = dH W_h ; dW_h = dH^T Z
+    {
+      GemmEpilogue ez;
+      ez.C = ws.dz; ez.ldc = D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dh, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, ez));
+      DRIN_TRY(weight_grad(stream, ws, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
+    }
+    LayerBwdArgs la{};
+    la.B = c.batch; la.C = c.candidates; la.D = D; la.full = lw.full;
+    for (int k = 0; k < 4; ++k) la.en[k] = c.edge_enabled[k];
+    la.xm = lw.xm;
+    if (l == 0) {
+      la.x_et = ws.x0 + 2 * B * D;
+      la.x_ei = ws.x0 + (2 * B + BC) * D;
+      la.edges_in = ws.edges0;
+      la.dcand_hi = ws.dx0.hi; la.dcand_lo = ws.dx0.lo;
+      la.dedges_in = nullptr;
+    } else {
+      const LayerWs& pw = ws.layer[l - 1];
+      la.x_et = pw.h + 2 * B * D;
+      la.x_ei = pw.h + (2 * B + BC) * D;
+      la.ln_gamma = p.layer[l - 1].ln_w;
+      la.ln_beta = p.layer[l - 1].ln_b;
+      la.edges_in = pw.edges_out;
+      la.dcand_hi = ws.dh.hi; la.dcand_lo = ws.dh.lo;
+      la.dedges_in = dedges[l % 2];
+    }
+    la.dz = ws.dz;
+    if (lw.full) {
+      la.g = lw.g;
+      la.edges_out = lw.edges_out;
+      la.dedges_out = dedges[(l + 1) % 2];
+      la.dg_hi = ws.dg_p.hi; la.dg_lo = ws.dg_p.lo;
+      la.dbeta = ws.dbeta;
+    }
+    la.dxm = ws.dxm;
+    la.partials = partA;
+    DRIN_TRY(gcn_layer_bwd(stream, la));
+
+    if (lw.full) {
+      // edge-update weights: fu = W_u xm + b_u, g = fu W_v, beta = fu . b_v
+      GemmEpilogue ef;
+      ef.C = ws.dfu; ef.ldc = D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.dg_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, ef));
+      DRIN_TRY(dfu_finish(stream, D, ws.dfu, ws.dbeta, lp.b_v, lw.fu, 2 * B, ws.dfu_p.hi, ws.dfu_p.lo, partB));
+      DRIN_TRY(colsum_reduce(stream, partB, nullptr, 2, D, lg.b_u, lg.b_v, nullptr));
+      DRIN_TRY(weight_grad(stream, ws, op(lw.fu_p, 2 * B, D), op(ws.dg_p, 2 * B, D), D, D, 2 * B, lg.w_v));
+      DRIN_TRY(weight_grad(stream, ws, op(ws.dfu_p, 2 * B, D), op(lw.xm_p, 2 * B, D), D, D, 2 * B, lg.w_u));
+      GemmEpilogue ex;
+      ex.C = ws.dxu; ex.ldc = D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dfu_p, 2 * B, D), op(lw.w_u, D, D), 2 * B, D, D, ex));
+    }
+    MentionBwdArgs ma{};
+    ma.B = c.batch; ma.D = D;
+    ma.dxm = ws.dxm;
+    ma.dxu = lw.full ? ws.dxu : nullptr;
+    if (l > 0) {
+      ma.h_prev = ws.layer[l - 1].h;
+      ma.ln_gamma = p.layer[l - 1].ln_w;
+      ma.ln_beta = p.layer[l - 1].ln_b;
+      ma.out_hi = ws.dh.hi; ma.out_lo = ws.dh.lo;
+    } else {
+      ma.out_hi = ws.dx0.hi; ma.out_lo = ws.dx0.lo;
+    }
+    ma.partials = partB;
+    DRIN_TRY(mention_bwd_finish(stream, ma));
+    if (l > 0) {
+      const drin_layer_params& pg = grads.layer[l - 1];
+      DRIN_TRY(colsum_reduce(stream, partA, partB, 3, D, pg.ln_w, pg.ln_b, pg.b_h));
+    } else {
+      DRIN_TRY(colsum_reduce(stream, partA, nullptr, 3, D, grads.b_et, grads.b_ei, nullptr));
+      DRIN_TRY(colsum_reduce(stream, partB, nullptr, 3, D, grads.b_mt, grads.b_mi, nullptr));
+    }
+  }
+
+  // input projections: dW = dX0^T A (no data gradient: the cached features are constants)
+  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, B, D, 0), op(ws.span, B, D), D, D, B, grads.w_mt));
+  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, B, D, B), op(ws.mim, B, R), D, R, B, grads.w_mi));
+  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, BC, D, 2 * B), op(ws.epool, BC, D), D, D, BC, grads.w_et));
+  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, BC, D, 2 * B + BC), op(ws.eimg, BC, R), D, R, BC, grads.w_ei));
+  return DRIN_OK;
+}
+
+}  // namespace drin

@@ -52,4 +52,62 @@ int rowdot(cudaStream_t stream, int D, const float* x, long long rows, const flo
 int score_fwd(cudaStream_t stream, int D, const float* h_mt, const float* h_et, const float* gamma, const float* beta,
               int B, int C, float* scores);
 
+// gcn_bwd.cu
+struct ScoreBwdArgs {
+  int B, C, D;
+  const float* h_mt;       // [B, D]  pre-LN rows of the last layer
+  const float* h_et;       // [BC, D]
+  const float* gamma; const float* beta;
+  const float* dscores;    // [B, C]
+  bf16* dh_hi; bf16* dh_lo;   // [B+BC, D] (mt rows, then et rows)
+  float* partials;         // [ctas][3][D]: dgamma, dbeta, db_h
+};
+int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a);
+
+struct LayerBwdArgs {
+  int B, C, D;
+  bool full;
+  float en[4];
+  const float* xm;            // [2B, D]
+  const float* x_et; const float* x_ei; const float* ln_gamma; const float* ln_beta;   // as in LayerFwdArgs
+  const float* edges_in;      // [4, BC]
+  const float* dz;            // [rows, D] gradient w.r.t. z in this layer's row layout
+  const float* g;             // [2B, D]   (full)
+  const float* edges_out;     // [4, BC]   (full) sigmoid outputs
+  const float* dedges_out;    // [4, BC]   (full) gradient w.r.t. edges_out
+  bf16* dcand_hi; bf16* dcand_lo;   // candidate-row gradients in the [mt; mi; et; ei] layout (rows 2B..)
+  float* dxm;                 // [2B, D] partial mention-row gradient
+  float* dedges_in;           // [4, BC] or null (first layer: edges are inputs)
+  bf16* dg_hi; bf16* dg_lo;   // [2B, D]   (full)
+  float* dbeta;               // [2B]      (full)
+  float* partials;            // [ctas][3][D]: ln -> (dgamma, dbeta, db_h) of the previous layer; else (db_et, db_ei, -)
+};
+int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a);
+
+struct MentionBwdArgs {
+  int B, D;
+  const float* dxm;           // [2B, D]
+  const float* dxu;           // [2B, D] or null
+  const float* h_prev;        // [2B, D] pre-LN mention rows of the previous layer (ln)
+  const float* ln_gamma; const float* ln_beta;
+  bf16* out_hi; bf16* out_lo; // [2B, D] dh of the previous layer (ln) or dx0 (first layer)
+  float* partials;            // [ctas][3][D]: ln -> (dgamma, dbeta, db_h); else (db_mt, db_mi, -)
+};
+int mention_bwd_finish(cudaStream_t stream, const MentionBwdArgs& a);
+int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const float* b_v, const float* fu,
+               long long rows, bf16* out_hi, bf16* out_lo, float* partials);
+int colsum_reduce(cudaStream_t stream, const float* src0, const float* src1, int nvec, int D, float* out0, float* out1,
+                  float* out2);
+int backward_ctas();
+
+// loss.cu
+size_t triplet_scratch_bytes(int B, int C);
+int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* labels, int B, int C, int row0,
+                 int rows, float margin, float* loss, float* dscores, void* scratch);
+int topk_hits(cudaStream_t stream, const float* scores, const unsigned char* labels, int B, int C, const int* topk,
+              int nk, long long* hits);
+// adam.cu
+int adam_step(cudaStream_t stream, float* p, const float* g, float* m, float* v, const unsigned char* skip, long long n,
+              int step, float lr, float b1, float b2, float eps);
+
 }  // namespace drin

@@ -107,7 +107,8 @@ int drin_backward(const drin_config* cfg, const drin_inputs* in, const drin_para
  * [row_offset, row_offset + rows_local) of a global score matrix (data-parallel: scores of all ranks are
  * gathered first, because the loss couples every mention with every score of the batch).
  *   scores_all [B_glob, C] fp32, labels_all [B_glob, C-1] uint8 one-hot (all-zero row = gold not listed)
- *   loss       [1]   fp32 global loss (identical on every rank)
+ *   loss       [1]   fp32: this call's share of the global loss, i.e. the sum over the local rows' scores
+ *                    (the shares of all ranks add up to the reference loss; single rank: the loss itself)
  *   dscores    [rows_local, C] fp32 gradient of the GLOBAL loss w.r.t. the local rows (gold slot = 0)
  *   scratch    >= drin_loss_scratch_bytes(B_glob, C) bytes */
 int drin_loss_scratch_bytes(int32_t batch_global, int32_t candidates, size_t* bytes);
