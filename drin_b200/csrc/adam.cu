@@ -28,6 +28,7 @@ __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g
 
 int adam_step(cudaStream_t stream, float* p, const float* g, float* m, float* v, const unsigned char* skip, long long n,
               int step, float lr, float b1, float b2, float eps) {
+  prof::Scope prof_scope(stream, prof::ADAM);
   if (n % 4) return fail(DRIN_ERR_ARG, "adam_step: n must be a multiple of 4");
   if (step < 1) return fail(DRIN_ERR_ARG, "adam_step: step is 1-based");
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);

@@ -77,6 +77,14 @@ int drin_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   return adam_step((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, skip_mask, n, step, lr, beta1, beta2, eps);
 }
 
+long long drin_launch_count(void) { return launch_count(); }
+void drin_profile_enable(int32_t on) { prof::enable(on != 0); }
+int drin_profile_collect(double* ms, double* flops, double* bytes, long long* count) {
+  if (!ms || !flops || !bytes || !count) return fail(DRIN_ERR_ARG, "drin_profile_collect: null argument");
+  prof::collect(ms, flops, bytes, count);
+  return DRIN_OK;
+}
+
 int drin_frontend(const drin_config* cfg, const drin_inputs* in, float* span, float* mimean, float* epool,
                   float* edges, void* stream) {
   if (!cfg || !in) return fail(DRIN_ERR_ARG, "drin_frontend: null argument");

@@ -27,7 +27,13 @@ int fail(int code, const char* fmt, ...);   // records the message, returns `cod
                           cudaGetErrorString(e__));                                        \
   } while (0)
 
-#define DRIN_LAUNCH_CHECK() DRIN_CUDA(cudaGetLastError())
+void count_launch();          // prof.cu: every kernel launch of this library is counted
+long long launch_count();
+#define DRIN_LAUNCH_CHECK()          \
+  do {                               \
+    ::drin::count_launch();          \
+    DRIN_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define DRIN_TRY(expr)                 \
   do {                                 \

@@ -20,6 +20,7 @@ __global__ void split_planes_kernel(const float4* __restrict__ x, uint2* __restr
 }
 
 int split_planes(cudaStream_t stream, const float* x, bf16* hi, bf16* lo, long long n) {
+  prof::Scope prof_scope(stream, prof::PREP);
   if (n % 4) return fail(DRIN_ERR_ARG, "split_planes: n must be a multiple of 4 (got %lld)", n);
   if (n == 0) return DRIN_OK;
   const long long n4 = n / 4;

@@ -311,6 +311,7 @@ static int launch_frontend(cudaStream_t stream, const FrontendArgs& a) {
 }
 
 int frontend(cudaStream_t stream, const FrontendArgs& a, bool bf16_features) {
+  prof::Scope prof_scope(stream, prof::FRONTEND);
   if (a.D % 256 || a.R % 256) return fail(DRIN_ERR_ARG, "frontend: D and R must be multiples of 256");
   if (a.Om > FE_MAX_OM) return fail(DRIN_ERR_ARG, "frontend: at most %d mention objects", FE_MAX_OM);
   if (a.B <= 0 || a.C <= 0) return fail(DRIN_ERR_ARG, "frontend: empty batch");

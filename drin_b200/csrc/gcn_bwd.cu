@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(NW * 32) score_bwd_kernel(const ScoreBwdArgs a
 }
 
 int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a) {
+  prof::Scope prof_scope(stream, prof::SCORE);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "score_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
   const size_t smem = (size_t)(3 + BW_NW + 3 * BW_NW) * D * sizeof(float);
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdAr
 }
 
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
+  prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
   const size_t smem = (size_t)(8 + 7 * BW_NW) * D * sizeof(float);
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(NW * 32) mention_bwd_finish_kernel(const Menti
 }
 
 int mention_bwd_finish(cudaStream_t stream, const MentionBwdArgs& a) {
+  prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "mention_bwd_finish: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
   const size_t smem = (size_t)(2 + 3 * BW_NW) * D * sizeof(float);
@@ -460,6 +463,7 @@ __global__ void __launch_bounds__(NW * 32) dfu_finish_kernel(float* __restrict__
 
 int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const float* b_v, const float* fu,
                long long rows, bf16* out_hi, bf16* out_lo, float* partials) {
+  prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (D != 768) return fail(DRIN_ERR_ARG, "dfu_finish: gcn_embed_dim %d not built (768 only)", D);
   const size_t smem = (size_t)(1 + 2 * BW_NW) * 768 * sizeof(float);
   dfu_finish_kernel<768, BW_NW><<<BW_CTAS, BW_NW * 32, smem, stream>>>(dfu, dbeta, b_v, fu, rows, out_hi, out_lo,
@@ -487,6 +491,7 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ src0, const float
 
 int colsum_reduce(cudaStream_t stream, const float* src0, const float* src1, int nvec, int D, float* out0, float* out1,
                   float* out2) {
+  prof::Scope prof_scope(stream, prof::GCN_BWD);
   const int n = nvec * D;
   colsum_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(src0, src1, BW_CTAS, nvec, D, out0, out1, out2);
   DRIN_LAUNCH_CHECK();

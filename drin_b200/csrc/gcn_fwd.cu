@@ -154,6 +154,7 @@ static int launch_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
 }
 
 int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
+  prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: gcn_embed_dim %d not built (768 only)", a.D);
   return a.C < 32 ? launch_layer_fwd<768, 4>(stream, a) : launch_layer_fwd<768, 8>(stream, a);
 }
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(256) mention_ln_kernel(const float* __restrict
 
 int mention_ln(cudaStream_t stream, int D, const float* h, long long rows, const float* gamma, const float* beta,
                float* x, bf16* x_hi, bf16* x_lo) {
+  prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (D != 768) return fail(DRIN_ERR_ARG, "mention_ln: gcn_embed_dim %d not built (768 only)", D);
   const long long blocks = (rows + 7) / 8;
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x
 }
 
 int rowdot(cudaStream_t stream, int D, const float* x, long long rows, const float* w, float* out) {
+  prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (D != 768) return fail(DRIN_ERR_ARG, "rowdot: gcn_embed_dim %d not built (768 only)", D);
   const long long blocks = (rows + 7) / 8;
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(NW * 32) score_kernel(const float* __restrict_
 
 int score_fwd(cudaStream_t stream, int D, const float* h_mt, const float* h_et, const float* gamma, const float* beta,
               int B, int C, float* scores) {
+  prof::Scope prof_scope(stream, prof::SCORE);
   if (D != 768) return fail(DRIN_ERR_ARG, "score: gcn_embed_dim %d not built (768 only)", D);
   const int grid = B < 148 * 8 ? B : 148 * 8;
   if (C < 32) score_kernel<768, 4><<<grid, 128, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);

@@ -19,6 +19,7 @@
 #include <unordered_map>
 
 #include "gemm.cuh"
+#include "kernels.cuh"
 
 namespace drin {
 
@@ -505,6 +506,7 @@ static int gemm_init_once() {
 
 int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M, int N,
                  long long K, const GemmEpilogue& ep, int ksplit, float* partial) {
+  prof::Scope prof_scope(stream, prof::GEMM, 2.0 * (double)M * (double)N * (double)K, 0);
   DRIN_TRY(gemm_init_once());
   if (M <= 0 || N <= 0 || K <= 0) return fail(DRIN_ERR_ARG, "gemm: empty problem M=%lld N=%d K=%lld", M, N, K);
   const int planes = A.lo ? 2 : 1;

@@ -7,6 +7,20 @@ namespace drin {
 
 const char* last_error();
 
+// prof.cu
+namespace prof {
+enum Cat { GEMM = 0, FRONTEND = 1, GCN_FWD = 2, GCN_BWD = 3, SCORE = 4, LOSS = 5, ADAM = 6, PREP = 7, NCAT = 8 };
+void enable(bool on);
+bool enabled();
+struct Scope {
+  Scope(cudaStream_t s, int cat, double flops = 0, double bytes = 0);
+  ~Scope();
+  cudaStream_t stream_;
+  int idx_;
+};
+int collect(double* ms, double* flops, double* bytes, long long* count);
+}  // namespace prof
+
 // elementwise.cu
 int split_planes(cudaStream_t stream, const float* x, bf16* hi, bf16* lo, long long n);
 

@@ -141,6 +141,7 @@ __global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const
 
 int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* labels, int B, int C, int row0,
                  int rows, float margin, float* loss, float* dscores, void* scratch) {
+  prof::Scope prof_scope(stream, prof::LOSS);
   if (B <= 0 || C <= 1 || row0 < 0 || rows <= 0 || row0 + rows > B)
     return fail(DRIN_ERR_ARG, "triplet_loss: bad shape B=%d C=%d row0=%d rows=%d", B, C, row0, rows);
   if (!scores || !labels || !loss || !dscores || !scratch) return fail(DRIN_ERR_ARG, "triplet_loss: null argument");

@@ -30,39 +30,45 @@ def make_batch(
     signed_images: bool = False,              # N(0,1) variant instead of post-ReLU |N(0,1)|
     device: str = "cpu",
     pin: bool = False,
+    generate_on_device: bool = False,
 ) -> List[torch.Tensor]:
     if num_candidates is None:
         num_candidates = 10 if dataset == WIKIDIVERSE else 100
     B, C = batch_size, num_candidates + 1       # +1: the appended gold slot (prepare.py:86,181)
-    g = torch.Generator().manual_seed(seed)
+    # device="cpu": the values every parity test and golden fixture is built on.  A CUDA device generates
+    # on the GPU (same distributions, different values) so benchmarks need not spend minutes in CPU randn.
+    gen_dev = "cpu" if (device == "cpu" or not generate_on_device) else device
+    g = torch.Generator(device=gen_dev).manual_seed(seed)
+    _randn, _rand, _randint, _arange, _eye, _zeros, _ones = (torch.randn, torch.rand, torch.randint, torch.arange,
+                                                             torch.eye, torch.zeros, torch.ones)
 
     def randn(*s):
-        return torch.randn(*s, generator=g)
+        return _randn(*s, generator=g, device=gen_dev)
 
     def img(*s):
         x = randn(*s)
         return x if signed_images else x.abs()
 
     def scores(*s):
-        x = torch.rand(*s, generator=g)
-        return x * (torch.rand(*s, generator=g) >= 0.1)     # ~10 % exact zeros (resnet.py:117-118)
+        x = _rand(*s, generator=g, device=gen_dev)
+        return x * (_rand(*s, generator=g, device=gen_dev) >= 0.1)     # ~10 % exact zeros (resnet.py:117-118)
 
     mtf = randn(B, mention_tokens, bert_dim)
-    mmask = torch.ones(B, mention_tokens, dtype=torch.int64)
-    start = torch.randint(1, 20, (B,), generator=g)
-    end = torch.clamp(start + torch.randint(1, 6, (B,), generator=g), max=mention_tokens)
+    mmask = _ones(B, mention_tokens, dtype=torch.int64, device=gen_dev)
+    start = _randint(1, 20, (B,), generator=g, device=gen_dev)
+    end = torch.clamp(start + _randint(1, 6, (B,), generator=g, device=gen_dev), max=mention_tokens)
     mif = img(B, regions, resnet_dim)
     mof = img(B, mention_objects, 1, resnet_dim)
     mos = scores(B, mention_objects)
     if dataset == WIKIDIVERSE:
         etf = randn(B, C, bert_dim)
-        emask = torch.zeros(B, dtype=torch.int64)            # collated int 0 (data.py:86)
+        emask = _zeros(B, dtype=torch.int64, device=gen_dev)            # collated int 0 (data.py:86)
         eif = img(B, C, resnet_dim)
         eof = img(B, C, entity_objects, resnet_dim)
     elif dataset == WIKIMEL:
         etf = randn(B, C, entity_tokens, bert_dim)
-        n = torch.randint(4, entity_tokens + 1, (B, C, 1), generator=g)
-        emask = (torch.arange(entity_tokens).view(1, 1, -1) < n).to(torch.int64)
+        n = _randint(4, entity_tokens + 1, (B, C, 1), generator=g, device=gen_dev)
+        emask = (_arange(entity_tokens, device=gen_dev).view(1, 1, -1) < n).to(torch.int64)
         eif = img(B, C, 1, resnet_dim)
         eof = img(B, C, entity_objects, 1, resnet_dim)
     else:
@@ -71,13 +77,13 @@ def make_batch(
     miet = 20 + 5 * randn(B, C)
     mtei = 20 + 5 * randn(B, C)
     # answer in 0..C-1; value C-1 = "gold not among the candidates" -> all-zero label row (data.py:159-161)
-    ans = torch.randint(0, C, (B,), generator=g)
-    onehot = torch.cat([torch.eye(C - 1, dtype=torch.uint8), torch.zeros(1, C - 1, dtype=torch.uint8)])
+    ans = _randint(0, C, (B,), generator=g, device=gen_dev)
+    onehot = torch.cat([_eye(C - 1, dtype=torch.uint8, device=gen_dev), _zeros(1, C - 1, dtype=torch.uint8, device=gen_dev)])
     y = onehot[ans]
     out = [mtf, mmask, start, end, mif, mof, mos, etf, emask, eif, eof, eos, miet, mtei, y]
     if pin:
         out = [t.pin_memory() for t in out]
-    if device != "cpu":
+    if device != "cpu" and gen_dev == "cpu":
         out = [t.to(device, non_blocking=True) for t in out]
     return out
 

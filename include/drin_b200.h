@@ -147,6 +147,15 @@ void drin_gemm_debug_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes);
 int drin_frontend(const drin_config* cfg, const drin_inputs* in, float* span, float* mimean, float* epool,
                   float* edges, void* stream);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched so far, and per-stage device
+ * time from CUDA events recorded on the launching stream.  Stage ids: 0 GEMM (flops = 2MNK per launch),
+ * 1 front end, 2 GCN forward, 3 GCN backward, 4 scoring fwd/bwd, 5 loss, 6 Adam, 7 weight/plane prep.
+ * drin_profile_collect fills four arrays of DRIN_PROFILE_STAGES entries and resets the records. */
+#define DRIN_PROFILE_STAGES 8
+long long drin_launch_count(void);
+void drin_profile_enable(int32_t on);
+int drin_profile_collect(double* ms, double* flops, double* bytes, long long* count);
+
 /* Test hook: device pointer / shape of a named fp32 intermediate ("edges0", "x0", "h", "xm", "fu", "g",
  * "edges_out", "dz") inside a workspace planned for cfg.  Not part of the drop-in surface. */
 int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name, int32_t layer, void** ptr,
