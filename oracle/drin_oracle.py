@@ -270,3 +270,22 @@ def adam_step(params: Dict[str, Tensor], grads: Dict[str, Tensor], state: dict, 
         bc1, bc2 = 1 - betas[0] ** t, 1 - betas[1] ** t
         denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
         p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+def triplet_sharded(scores_all: Tensor, labels_all: Tensor, margin: float, row0: int, rows: int):
+    """Data-parallel form of the loss, closed form.  Returns (this shard's share of the global
+    loss, d(global loss)/d(scores of rows row0..row0+rows)) with
+        dL/ds[b,c] = k * (A[b,c] - y[b,c] * N_b),  k = 1 / (B * B * (C-1)),
+        A[b,c] = #{i : s[b,c] - p_i + margin > 0},  N_b = #{(b',c') : s[b',c'] - p_b + margin > 0}."""
+    s = scores_all[:, :-1]
+    y = labels_all.to(s.dtype)
+    B, Cm1 = s.shape
+    k = 1.0 / (B * B * Cm1)
+    p = (s * y).sum(-1)
+    sl = s[row0:row0 + rows]
+    active = (sl.unsqueeze(-1) - p.view(1, 1, -1) + margin) > 0                  # [rows, C-1, B]
+    share = k * (sl.unsqueeze(-1) - p.view(1, 1, -1) + margin).clamp_min(0).sum()
+    A = active.sum(-1).to(s.dtype)
+    N = ((s.unsqueeze(0) - p[row0:row0 + rows].view(-1, 1, 1) + margin) > 0).sum((1, 2)).to(s.dtype)
+    d = k * (A - y[row0:row0 + rows] * N.unsqueeze(1))
+    return share, torch.cat([d, torch.zeros(rows, 1, dtype=s.dtype)], dim=1)

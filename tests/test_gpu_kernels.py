@@ -1,0 +1,162 @@
+"""Stage-level parity through the C ABI: tcgen05 GEMM (3 layouts x 2 modes), front end, loss, metric, Adam."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+import drin_b200
+from drin_b200 import _lib, engine as E
+from drin_b200.synthetic import make_batch
+from oracle import drin_oracle as O
+from tests.helpers import GOLDEN_DIR, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _gemm(layout, planes, M, N, K, ksplit=1, bias=False, want_planes=False, reference=0):
+    lib = _lib.load()
+    torch.manual_seed(M + N + K)
+    a = torch.randn((K, M) if layout == 2 else (M, K), device="cuda")
+    b = torch.randn((N, K) if layout == 0 else (K, N), device="cuda")
+
+    def split(x):
+        hi = x.to(torch.bfloat16)
+        return hi, ((x - hi.float()).to(torch.bfloat16) if planes == 2 else None)
+
+    (a_hi, a_lo), (b_hi, b_lo) = split(a), split(b)
+    a_eff = a_hi.double() + (a_lo.double() if a_lo is not None else 0)
+    b_eff = b_hi.double() + (b_lo.double() if b_lo is not None else 0)
+    ref = (a_eff.t() if layout == 2 else a_eff) @ (b_eff.t() if layout == 0 else b_eff)
+    bias_t = torch.randn(N, device="cuda") if bias else None
+    if bias:
+        ref = ref + bias_t.double()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    oh = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda") if want_planes else None
+    ol = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda") if want_planes else None
+    partial = torch.empty(ksplit * M * N, device="cuda") if ksplit > 1 else None
+    st = lib.drin_gemm(C.c_int32(layout), _p(a_hi), _p(a_lo), C.c_int32(a.shape[1]), _p(b_hi), _p(b_lo),
+                       C.c_int32(b.shape[1]), C.c_int64(M), C.c_int32(N), C.c_int64(K), _p(out), C.c_int32(N),
+                       _p(bias_t), _p(oh), _p(ol), C.c_int32(N), C.c_int32(ksplit), _p(partial), C.c_int32(reference),
+                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "drin_gemm")
+    torch.cuda.synchronize()
+    err = rel_err(out, ref)
+    perr = rel_err(oh.double() + ol.double(), ref) if want_planes else None
+    return err, perr
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("planes", [1, 2])
+def test_gemm_layouts(layout, planes):
+    """NT / NN / TN, ragged M (TMA zero fill + masked epilogue), K tails, bias, plane outputs."""
+    tol = 2e-5 if planes == 2 else 5e-6     # operands are pre-rounded: only accumulation order differs
+    for (M, N, K) in ((128, 256, 64), (300, 768, 768), (77, 768, 2048), (768, 768, 1000)):
+        if layout == 2:
+            M = (M + 7) // 8 * 8          # A is stored [K, M]: TMA needs a 16-byte row pitch
+        err, perr = _gemm(layout, planes, M, N, K, bias=(layout == 0), want_planes=(planes == 2 and layout != 2))
+        assert err < tol, (layout, planes, M, N, K, err)
+        if perr is not None:
+            assert perr < 3e-5
+
+
+def test_gemm_split_k_is_deterministic_and_exact():
+    e1, _ = _gemm(2, 2, 768, 2048, 5000, ksplit=3)
+    e2, _ = _gemm(2, 2, 768, 768, 9000, ksplit=8)
+    assert e1 < 2e-5 and e2 < 2e-5
+
+
+def test_gemm_reference_kernel_agrees():
+    err, _ = _gemm(0, 2, 200, 512, 512, reference=1)
+    assert err < 5e-6
+
+
+@pytest.mark.parametrize("dataset,kw", [("wikidiverse", {}), ("wikimel", {}),
+                                        ("wikimel", dict(num_candidates=5, entity_tokens=16, mention_tokens=32))])
+def test_frontend_stage(dataset, kw):
+    """drin_frontend vs the oracle: span mean, region mean, entity pooling, tt / ii edges, CLIP edges / 100."""
+    B = 5
+    batch = make_batch(dataset, B, 11, **kw)
+    db = [t.cuda() for t in batch[:-1]]
+    pb = E.inspect_batch(db)
+    eng = E.Engine(2)
+    cfg = eng.config(pb, False)
+    span = torch.empty(pb.B, pb.D, device="cuda")
+    mim = torch.empty(pb.B, pb.R, device="cuda")
+    ep = torch.empty(pb.B * pb.C, pb.D, device="cuda")
+    edges = torch.empty(4, pb.B * pb.C, device="cuda")
+    ins = eng.inputs(db)
+    _lib.check(eng.lib.drin_frontend(C.byref(cfg), C.byref(ins), _p(span), _p(mim), _p(ep), _p(edges),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "drin_frontend")
+    torch.cuda.synchronize()
+    b = batch[:-1]
+    assert rel_err(span.cpu(), O.span_mean(b[0], b[2], b[3])) < 1e-6
+    assert rel_err(mim.cpu(), b[4].mean(-2)) < 1e-6
+    assert rel_err(ep.cpu(), O.entity_text_pool(b[7], b[8]).flatten(0, 1)) < 1e-6
+    tt, ii = O.edge_encode(b)
+    want = torch.stack([tt.flatten(), (b[13] / 100).flatten(), (b[12] / 100).flatten(), ii.flatten()])
+    assert rel_err(edges.cpu(), want) < 2e-6
+    # zero object scores are legal: ii = 0 / (0 + 1e-9) = 0
+    z = [t.clone() for t in db]
+    z[6].zero_()
+    ins = eng.inputs(z)
+    _lib.check(eng.lib.drin_frontend(C.byref(cfg), C.byref(ins), _p(span), _p(mim), _p(ep), _p(edges),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "drin_frontend")
+    assert float(edges[3].abs().max()) == 0.0
+
+
+def test_triplet_loss_and_topk_against_reference_fixtures():
+    cases = torch.load(os.path.join(GOLDEN_DIR, "triplet_loss_cases.pt"), weights_only=False)
+    for c in cases:
+        s = c["scores"].cuda().requires_grad_(True)
+        loss = drin_b200.TripletLoss(c["margin"])(c["labels"].cuda(), s)
+        loss.backward()
+        assert abs(float(loss) - float(c["loss"])) <= 1e-6 * max(1.0, abs(float(c["loss"])))
+        assert rel_err(s.grad.cpu(), c["dscores"]) < 1e-5
+        assert float(s.grad[:, -1].abs().max()) == 0.0
+        met = drin_b200.TopkAccuracy([1, 3, 5])
+        met.update(s.detach(), c["labels"].cuda())
+        assert met.correct.tolist() == [c["topk_hits"][k] for k in (1, 3, 5)]
+
+
+def test_sharded_loss_equals_global_loss():
+    """Data-parallel form: shares of the loss add up, local gradient rows equal the global ones (bitwise)."""
+    from drin_b200.loss import triplet_loss_sharded
+    g = torch.Generator().manual_seed(5)
+    B, Cn = 64, 11
+    s = (torch.rand(B, Cn, generator=g) * 2 - 1).cuda()
+    y = torch.eye(Cn - 1, dtype=torch.uint8)[torch.randint(0, Cn - 1, (B,), generator=g)].cuda()
+    full_loss, full_d = triplet_loss_sharded(s, y, 0.25)
+    full_loss, full_d = full_loss.clone(), full_d.clone()
+    parts, shares = [], []
+    for r in range(4):
+        l, d = triplet_loss_sharded(s, y, 0.25, r * 16, 16)
+        parts.append(d.clone())
+        shares.append(float(l))
+    assert torch.equal(torch.cat(parts), full_d)
+    assert abs(sum(shares) - float(full_loss)) < 1e-6 * abs(float(full_loss))
+    ref = O.triplet_loss(y.cpu(), s.cpu(), 0.25)
+    assert abs(float(full_loss) - float(ref)) < 1e-6 * abs(float(ref))
+
+
+def test_fused_adam_matches_torch_adam():
+    torch.manual_seed(0)
+    model = drin_b200.Model().cuda()
+    ref = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    names = [n for n, _ in model.named_parameters()]
+    dead = set(E.dead_param_keys(2))
+    opt_ref = torch.optim.Adam(ref, lr=1e-3)
+    opt = drin_b200.FusedAdam(model, lr=1e-3)
+    for step in range(3):
+        g = torch.randn_like(model.flat_params) * (10.0 ** (-step))
+        model.flat_grads.copy_(g)
+        for n, r, (o, cnt, shape) in zip(names, ref, [model._offsets[n] for n in names]):
+            r.grad = None if n in dead else g[o:o + cnt].view(shape).clone()
+        opt.step()
+        opt_ref.step()
+    for n, p, r in zip(names, model.parameters(), ref):
+        assert torch.allclose(p.detach(), r.detach(), rtol=2e-6, atol=1e-8), n

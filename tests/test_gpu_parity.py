@@ -1,0 +1,134 @@
+"""Parity of the CUDA path (through the C ABI / drop-in Model) against
+  (a) the committed golden outputs of the UNMODIFIED reference (tests/golden/*.pt), and
+  (b) the CPU oracle on the same seeded inputs.
+Tolerance (BASELINE.json): scores, loss and gradients within 1e-4 relative in fp32 mode; identical
+top-1/top-k rankings.  "Relative" = max |a-b| / max |b| per tensor (tests/helpers.rel_err)."""
+import os
+
+import pytest
+import torch
+
+import drin_b200
+from oracle import drin_oracle as O
+from tests.helpers import golden_model_cases, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+CASES = golden_model_cases()
+TOL = 1e-4
+
+
+def _cuda_model(cfg, sd):
+    m = drin_b200.Model(num_gcn_layers=cfg.num_gcn_layers, gcn_edge_enabled=cfg.gcn_edge_enabled,
+                        num_candidates_model=cfg.num_candidates_model)
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-3] for p in CASES])
+def test_train_step_matches_reference_golden_and_oracle(path):
+    cfg, batch, sd, fx = load_case(path)
+    model = _cuda_model(cfg, sd)
+    dbatch = [t.cuda() for t in batch]
+    scores = model(dbatch[:-1])                                   # the reference's forward signature
+    loss = drin_b200.TripletLoss(cfg.triplet_margin)(dbatch[-1], scores)
+    loss.backward()
+    # (a) golden outputs of the real reference
+    assert rel_err(scores.detach().cpu(), fx["scores"]) < TOL
+    assert abs(float(loss) - fx["loss"]) <= TOL * abs(fx["loss"])
+    assert torch.equal(O.ranking(scores.detach().cpu()), O.ranking(fx["scores"]))
+    met = drin_b200.TopkAccuracy(sorted(fx["topk_hits"]))
+    met.update(scores.detach(), dbatch[-1])
+    assert met.correct.tolist() == [fx["topk_hits"][k] for k in sorted(fx["topk_hits"])]
+    for key, p in model.named_parameters():
+        g = fx["grads"][key]
+        if g is None:
+            assert p.grad is None, f"{key}: the reference gives grad None (dead edge update of the last layer)"
+            continue
+        got = p.grad.flatten().cpu()
+        assert abs(float(got.double().norm()) - g["norm"]) <= TOL * g["norm"] + 1e-12, key
+    # (b) full gradient tensors against the oracle
+    _, _, grads = O.train_step_grads(sd, batch[:-1], batch[-1], cfg)
+    for key, p in model.named_parameters():
+        if grads[key] is not None:
+            assert rel_err(p.grad.cpu(), grads[key]) < TOL, key
+
+
+@pytest.mark.parametrize("path", CASES[:4], ids=[os.path.basename(p)[:-3] for p in CASES[:4]])
+def test_ranking_forward_no_grad(path):
+    cfg, batch, sd, fx = load_case(path)
+    model = _cuda_model(cfg, sd)
+    with torch.no_grad():
+        scores = model([t.cuda() for t in batch[:-1]])
+    assert not scores.requires_grad
+    assert rel_err(scores.cpu(), fx["scores"]) < TOL
+    assert torch.equal(O.ranking(scores.cpu()), O.ranking(fx["scores"]))
+
+
+def test_fused_trainer_equals_autograd_path():
+    cfg, batch, sd, fx = load_case(CASES[0])
+    dbatch = [t.cuda() for t in batch]
+    m1, m2 = _cuda_model(cfg, sd), _cuda_model(cfg, sd)
+    s = m1(dbatch[:-1])
+    drin_b200.TripletLoss(cfg.triplet_margin)(dbatch[-1], s).backward()
+    tr = drin_b200.Trainer(m2, margin=cfg.triplet_margin)
+    loss = tr.forward_backward(dbatch)
+    assert abs(float(loss) - fx["loss"]) <= TOL * abs(fx["loss"])
+    fused = m2._grad_views()
+    for k, p in m1.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, fused[k]), k            # same kernels, same order: bit identical
+
+
+def test_loss_trajectory_over_adam_steps():
+    """Five fused steps (fwd+loss+bwd+Adam) track the oracle's loss trajectory."""
+    cfg, batch, sd, _ = load_case(CASES[1])
+    dbatch = [t.cuda() for t in batch]
+    tr = drin_b200.Trainer(_cuda_model(cfg, sd), lr=1e-3, margin=cfg.triplet_margin)
+    params, st = {k: v.clone() for k, v in sd.items()}, {}
+    for _ in range(5):
+        _, l_ref, g = O.train_step_grads(params, batch[:-1], batch[-1], cfg)
+        O.adam_step(params, g, st)
+        l = tr.step(dbatch)
+        assert abs(float(l) - float(l_ref)) <= 2e-3 * abs(float(l_ref))   # Adam amplifies 1e-5 grad noise via m/sqrt(v)
+
+
+def test_bf16_feature_mode():
+    """bf16 features + single-pass bf16 GEMMs.  Oracle = fp32 reference math on the bf16-rounded features
+    (the reference has no bf16 path).  Stated tolerance: 2e-3 on scores, 3e-2 on gradients."""
+    cfg, batch, sd, _ = load_case(CASES[2])
+    feats = (0, 4, 5, 7, 9, 10)
+    rb = [t.to(torch.bfloat16).float() if i in feats else t for i, t in enumerate(batch)]
+    s_ref, l_ref, g_ref = O.train_step_grads(sd, rb[:-1], rb[-1], cfg)
+    model = _cuda_model(cfg, sd)
+    db = [t.cuda().to(torch.bfloat16) if i in feats else t.cuda() for i, t in enumerate(batch)]
+    scores = model(db[:-1])
+    loss = drin_b200.TripletLoss(cfg.triplet_margin)(db[-1], scores)
+    loss.backward()
+    assert rel_err(scores.detach().cpu(), s_ref) < 2e-3
+    assert abs(float(loss) - float(l_ref)) < 2e-3 * abs(float(l_ref))
+    for k, p in model.named_parameters():
+        if g_ref[k] is not None:
+            assert rel_err(p.grad.cpu(), g_ref[k]) < 3e-2, k
+
+
+def test_nan_propagates_like_reference():
+    """start == end -> mean of an empty slice -> NaN scores for that mention only."""
+    cfg, batch, sd, _ = load_case(CASES[0])
+    batch = [t.clone() for t in batch]
+    batch[3][0] = batch[2][0]
+    with torch.no_grad():
+        s = _cuda_model(cfg, sd)([t.cuda() for t in batch[:-1]]).cpu()
+    assert torch.isnan(s[0]).all() and not torch.isnan(s[1:]).any()
+
+
+def test_rejects_bad_batches():
+    cfg, batch, sd, _ = load_case(CASES[0])
+    model = _cuda_model(cfg, sd)
+    with pytest.raises(RuntimeError):                      # CPU batch: no silent fallback
+        model(batch[:-1])
+    bad = [t.cuda() for t in batch[:-1]]
+    bad[7] = bad[7][:, :5].contiguous()                    # wrong candidate count (reference: expand() error)
+    with pytest.raises(RuntimeError):
+        model(bad)
+    with pytest.raises(ValueError):
+        model([t.cuda() for t in batch[:5]])

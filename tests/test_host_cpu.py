@@ -1,0 +1,83 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/drin_b200.h declares, the
+host-side mirror of the reference interface (constructor, state_dict, batch validation), no CPU fallback."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import drin_b200
+from drin_b200 import _lib, engine as E
+from drin_b200.synthetic import make_batch
+from oracle import drin_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "drin_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(drin_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/drin_b200.h but not exported"
+    assert lib.drin_version() >= 100
+
+
+def test_workspace_plan_and_config_errors_need_no_gpu():
+    eng = E.Engine(2)
+    pb = E.Problem(4096, 11, 128, 0, 49, 3, 1, 768, 2048, E.FP32)
+    infer, train = eng.workspace_bytes(eng.config(pb, False)), eng.workspace_bytes(eng.config(pb, True))
+    assert 0 < infer < train < 8 << 30
+    bad = eng.config(E.Problem(4, 11, 128, 0, 49, 3, 1, 512, 2048, E.FP32), False)
+    with pytest.raises(RuntimeError, match="gcn_embed_dim"):
+        eng.workspace_bytes(bad)
+
+
+def test_model_is_a_drop_in_for_the_reference_constructor():
+    torch.manual_seed(0)
+    m = drin_b200.Model()
+    sd = O.init_state(O.DrinConfig(), 0)             # pinned bit-for-bit to the reference init by make_golden.py
+    assert list(m.state_dict().keys()) == O.state_dict_keys(O.DrinConfig())
+    assert all(torch.equal(sd[k], v) for k, v in m.state_dict().items())
+    assert sum(p.numel() for p in m.parameters()) == 7_875_072
+    # parameters are views of one flat buffer and stay so across load_state_dict
+    m.load_state_dict({k: v * 2 for k, v in sd.items()})
+    assert torch.equal(m.flat_params[:768 * 768].view(768, 768), sd[O.K_MT_W] * 2)
+    assert int(m.dead_mask().sum()) == 2 * (768 * 768 + 768)
+
+
+def test_unsupported_configurations_fail_loudly():
+    for kw in (dict(gcn_edge_feature="vector"), dict(gcn_edge_type="static"), dict(gcn_vertex_activation="relu"),
+               dict(gcn_embed_dim=512)):
+        with pytest.raises(NotImplementedError):
+            drin_b200.Model(**kw)
+
+
+def test_no_cpu_fallback():
+    m = drin_b200.Model()
+    batch = make_batch("wikidiverse", 2, 0)
+    with pytest.raises(RuntimeError):
+        m(batch[:-1])
+    with pytest.raises(RuntimeError):
+        drin_b200.TripletLoss(0.25)(batch[-1], torch.zeros(2, 11))
+
+
+def test_install_as_reference_module():
+    import sys
+    drin_b200.install_as_reference_module()
+    from drin import model as model_module          # what reference train.py:13-14 does
+    assert model_module.Model is drin_b200.Model
+    del sys.modules["drin.model"], sys.modules["drin"]
+
+
+def test_param_key_tables():
+    assert E.param_keys(2) == O.state_dict_keys(O.DrinConfig())
+    assert E.dead_param_keys(2) == ["gcn_layers.1.w_u.weight", "gcn_layers.1.w_u.bias",
+                                    "gcn_layers.1.w_v.weight", "gcn_layers.1.w_v.bias"]
