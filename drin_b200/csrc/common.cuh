@@ -74,12 +74,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// exact-erf GELU (F.gelu default) and its derivative
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-based GELU (F.gelu default) and its derivative from ONE exp + ONE reciprocal:
+// erf(u) = 1 - (a1 t + .. + a5 t^5) exp(-u^2), t = 1 / (1 + p u)  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7),
+// and exp(-u^2) = exp(-x^2 / 2) is also the Gaussian density needed by the derivative.
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
+  const float ex = __expf(-u * u);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, ex, 1.0f);
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  g = x * cdf;
+  dg = fmaf(x * 0.3989422804014327f, ex, cdf);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float g, dg;
+  gelu_both(x, g, dg);
+  return g;
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float g, dg;
+  gelu_both(x, g, dg);
+  return dg;
 }
 #endif  // __CUDACC__
 

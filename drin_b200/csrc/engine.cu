@@ -104,7 +104,7 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
     // split-K: enough slices to fill the machine for the [D, D] weight gradients (18 tiles each)
     ws.ksplit = 8;
     ws.partial = m.take<float>((size_t)ws.ksplit * D * D > (size_t)3 * D * R ? (size_t)ws.ksplit * D * D : (size_t)3 * D * R);
-    ws.colsum_ctas = 148 * 2;
+    ws.colsum_ctas = backward_ctas();
     ws.colsum = m.take<float>((size_t)2 * ws.colsum_ctas * 3 * D);
   }
   ws.bytes = align_up(m.off, 256);

@@ -18,7 +18,7 @@
 namespace drin {
 
 static constexpr int BW_NW = 4;           // warps per CTA in the backward kernels
-static constexpr int BW_CTAS = 148 * 2;   // persistent grid (must match Workspace::colsum_ctas)
+static constexpr int BW_CTAS = 148 * 3;   // persistent grid (must match Workspace::colsum_ctas)
 
 template <int D>
 __device__ __forceinline__ void row_zero_smem(float* s, int lane) {
@@ -158,20 +158,87 @@ int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a) {
 // ---------------------------------------------------------------------------------------------
 // gcn_layer_bwd
 // ---------------------------------------------------------------------------------------------
+// One candidate vertex row (entity text or entity image) of one mention.  e_mt / e_mi are the enabled
+// edge weights linking the row to the mention text / image vertex, ds_mt / ds_mi the gradients w.r.t. the
+// pre-sigmoid edge updates of those two edges (full layers).  Returns the four un-reduced dot products
+// needed for the edge gradients.
+template <int D, bool FULL>
+__device__ __forceinline__ void layer_bwd_row(const float* __restrict__ xrow, const float* __restrict__ dzrow, bool ln,
+                                              const float* s_gamma, const float* s_beta, const float* s_xmt,
+                                              const float* s_xmi, const float* s_dzmt, const float* s_dzmi,
+                                              const float* s_gmt, const float* s_gmi, float e_mt, float e_mi,
+                                              float ds_mt, float ds_mi, float invC, float invD, float* accA_mt,
+                                              float* accA_mi, float* accG_mt, float* accG_mi, float* p0, float* p1,
+                                              float* p2, float* pbias, bf16* out_hi, bf16* out_lo, int lane,
+                                              float& pd_mt, float& pd_mi, float& q_mt, float& q_mi) {
+  const bool has_dz = dzrow != nullptr;
+  RowT<D> x, d;
+  row_load<D>(x, xrow, lane);
+  if (has_dz) {
+    row_load<D>(d, dzrow, lane);
+  } else {
+#pragma unroll
+    for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] = 0.f;
+  }
+  if (ln) row_ln_gelu<D>(x, s_gamma, s_beta, lane);
+  pd_mt = row_dot<D>(x, s_dzmt, lane);
+  pd_mi = FULL ? row_dot<D>(x, s_dzmi, lane) : 0.f;
+  q_mt = has_dz ? row_dot<D>(d, s_xmt, lane) : 0.f;
+  q_mi = has_dz ? row_dot<D>(d, s_xmi, lane) : 0.f;
+  const float ec_mt = e_mt * invC, ec_mi = e_mi * invC, dd_mt = ds_mt * invD, dd_mi = ds_mi * invD;
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    if (has_dz) {
+      float4 amt = *reinterpret_cast<float4*>(accA_mt + off);
+      float4 ami = *reinterpret_cast<float4*>(accA_mi + off);
+      amt.x += e_mt * d.v[4 * j]; amt.y += e_mt * d.v[4 * j + 1]; amt.z += e_mt * d.v[4 * j + 2]; amt.w += e_mt * d.v[4 * j + 3];
+      ami.x += e_mi * d.v[4 * j]; ami.y += e_mi * d.v[4 * j + 1]; ami.z += e_mi * d.v[4 * j + 2]; ami.w += e_mi * d.v[4 * j + 3];
+      *reinterpret_cast<float4*>(accA_mt + off) = amt;
+      *reinterpret_cast<float4*>(accA_mi + off) = ami;
+    }
+    const float4 zmt = *reinterpret_cast<const float4*>(s_dzmt + off);
+    d.v[4 * j] += ec_mt * zmt.x; d.v[4 * j + 1] += ec_mt * zmt.y; d.v[4 * j + 2] += ec_mt * zmt.z; d.v[4 * j + 3] += ec_mt * zmt.w;
+    if (FULL) {
+      const float4 zmi = *reinterpret_cast<const float4*>(s_dzmi + off);
+      const float4 gmt = *reinterpret_cast<const float4*>(s_gmt + off);
+      const float4 gmi = *reinterpret_cast<const float4*>(s_gmi + off);
+      float4 Gmt = *reinterpret_cast<float4*>(accG_mt + off);
+      float4 Gmi = *reinterpret_cast<float4*>(accG_mi + off);
+      Gmt.x += dd_mt * x.v[4 * j]; Gmt.y += dd_mt * x.v[4 * j + 1]; Gmt.z += dd_mt * x.v[4 * j + 2]; Gmt.w += dd_mt * x.v[4 * j + 3];
+      Gmi.x += dd_mi * x.v[4 * j]; Gmi.y += dd_mi * x.v[4 * j + 1]; Gmi.z += dd_mi * x.v[4 * j + 2]; Gmi.w += dd_mi * x.v[4 * j + 3];
+      *reinterpret_cast<float4*>(accG_mt + off) = Gmt;
+      *reinterpret_cast<float4*>(accG_mi + off) = Gmi;
+      d.v[4 * j] += ec_mi * zmi.x + dd_mt * gmt.x + dd_mi * gmi.x;
+      d.v[4 * j + 1] += ec_mi * zmi.y + dd_mt * gmt.y + dd_mi * gmi.y;
+      d.v[4 * j + 2] += ec_mi * zmi.z + dd_mt * gmt.z + dd_mi * gmi.z;
+      d.v[4 * j + 3] += ec_mi * zmi.w + dd_mt * gmt.w + dd_mi * gmi.w;
+    }
+  }
+  if (ln) {
+    row_load<D>(x, xrow, lane);                       // pre-LN row again (L1/L2 hit)
+    row_ln_gelu_bwd<D>(x, d, s_gamma, s_beta, p0, p1, lane);
+    row_accum_smem<D>(d, p2, lane);
+  } else {
+    row_accum_smem<D>(d, pbias, lane);                // first layer: bias gradient of the input projection
+  }
+  row_store_planes<D>(d, out_hi, out_lo, lane);
+}
+
 template <int D, int NW, bool FULL>
-__global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdArgs a) {
+__global__ void __launch_bounds__(NW * 32, FULL ? 2 : 3) gcn_layer_bwd_kernel(const LayerBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* s_xmt = sm;                       // activated mention vertices of this layer
   float* s_xmi = s_xmt + D;
-  float* s_dzmt = s_xmi + D;               // dL/dz of the mention rows
-  float* s_dzmi = s_dzmt + D;
-  float* s_gmt = s_dzmi + D;               // g = fu W_v (FULL)
-  float* s_gmi = s_gmt + D;
-  float* s_gamma = s_gmi + D;
+  float* s_dzmt = s_xmi + D;               // dL/dz of the mention text row
+  float* s_gamma = s_dzmt + D;
   float* s_beta = s_gamma + D;
-  float* s_acc = s_beta + D;               // [4][NW][D]: A_mt, A_mi, G_mt, G_mi
-  float* s_part = s_acc + 4 * NW * D;      // [3][NW][D]
-  __shared__ float s_db[2][NW];
+  float* s_part = s_beta + D;              // [3][NW][D]
+  float* s_acc = s_part + 3 * NW * D;      // [2 or 4][NW][D]: A_mt, A_mi, (G_mt, G_mi)
+  float* s_gmt = s_acc + (FULL ? 4 : 2) * NW * D;   // g = fu W_v (FULL)
+  float* s_gmi = s_gmt + D;
+  float* s_dzmi = s_gmi + D;               // dL/dz of the mention image row (FULL; zero in the last layer)
+  float* s_db = s_dzmi + D;                // [2][NW] per-warp dbeta partials (FULL)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long B = a.B, BC = (long long)a.B * a.C;
   const bool ln = a.ln_gamma != nullptr;
@@ -187,8 +254,8 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdAr
   float* p2 = s_part + (2 * NW + warp) * D;
   float* accA_mt = s_acc + (0 * NW + warp) * D;
   float* accA_mi = s_acc + (1 * NW + warp) * D;
-  float* accG_mt = s_acc + (2 * NW + warp) * D;
-  float* accG_mi = s_acc + (3 * NW + warp) * D;
+  float* accG_mt = FULL ? s_acc + (2 * NW + warp) * D : nullptr;
+  float* accG_mi = FULL ? s_acc + (3 * NW + warp) * D : nullptr;
   const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
   // row offsets of the dz blocks for this layer's layout
   const float* dz_mt = a.dz;
@@ -202,8 +269,8 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdAr
       s_xmt[i] = a.xm[(long long)b * D + i];
       s_xmi[i] = a.xm[(B + b) * D + i];
       s_dzmt[i] = dz_mt[(long long)b * D + i];
-      s_dzmi[i] = FULL ? dz_mi[(long long)b * D + i] : 0.f;
       if (FULL) {
+        s_dzmi[i] = dz_mi[(long long)b * D + i];
         s_gmt[i] = a.g[(long long)b * D + i];
         s_gmi[i] = a.g[(B + b) * D + i];
       }
@@ -219,113 +286,47 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdAr
 
     for (int c = warp; c < a.C; c += NW) {
       const long long r = (long long)b * a.C + c;
-      RowT<D> xet, xei, det, dei;
-      row_load<D>(xet, a.x_et + r * D, lane);
-      row_load<D>(xei, a.x_ei + r * D, lane);
-      if (ln) {
-        row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
-        row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
-      }
-      row_load<D>(det, dz_et + r * D, lane);
-      if (FULL) row_load<D>(dei, dz_ei + r * D, lane);
       const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
       const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
-      // dot products for the edge gradients
-      float pd0 = row_dot<D>(xet, s_dzmt, lane), pd1 = row_dot<D>(xei, s_dzmt, lane);
-      float q0 = row_dot<D>(det, s_xmt, lane), q2 = row_dot<D>(det, s_xmi, lane);
-      float pd2 = 0.f, pd3 = 0.f, q1 = 0.f, q3 = 0.f;
-      if (FULL) {
-        pd2 = row_dot<D>(xet, s_dzmi, lane);
-        pd3 = row_dot<D>(xei, s_dzmi, lane);
-        q1 = row_dot<D>(dei, s_xmt, lane);
-        q3 = row_dot<D>(dei, s_xmi, lane);
-      }
-      pd0 = warp_sum(pd0); pd1 = warp_sum(pd1); q0 = warp_sum(q0); q2 = warp_sum(q2);
-      if (FULL) { pd2 = warp_sum(pd2); pd3 = warp_sum(pd3); q1 = warp_sum(q1); q3 = warp_sum(q3); }
-      float de0 = pd0 * invC + q0, de1 = pd1 * invC + q1, de2 = pd2 * invC + q2, de3 = pd3 * invC + q3;
       float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
-      if (FULL) {
+      if (FULL) {   // through the sigmoid of the dynamic edge update
         const float o0 = a.edges_out[r], o1 = a.edges_out[BC + r], o2 = a.edges_out[2 * BC + r], o3 = a.edges_out[3 * BC + r];
         ds0 = a.dedges_out[r] * o0 * (1.f - o0);
         ds1 = a.dedges_out[BC + r] * o1 * (1.f - o1);
         ds2 = a.dedges_out[2 * BC + r] * o2 * (1.f - o2);
         ds3 = a.dedges_out[3 * BC + r] * o3 * (1.f - o3);
-        de0 += ds0; de1 += ds1; de2 += ds2; de3 += ds3;
         dbeta_mt += (ds0 + ds1) * invD;
         dbeta_mi += (ds2 + ds3) * invD;
       }
-      if (a.dedges_in && lane == 0) {
-        a.dedges_in[r] = de0 * a.en[0];
-        a.dedges_in[BC + r] = de1 * a.en[1];
-        a.dedges_in[2 * BC + r] = de2 * a.en[2];
-        a.dedges_in[3 * BC + r] = de3 * a.en[3];
-      }
-      // accumulators and candidate-row gradients
-#pragma unroll
-      for (int j = 0; j < RowT<D>::NV; ++j) {
-        const int off = (j * 32 + lane) * 4;
-        float4 amt = *reinterpret_cast<float4*>(accA_mt + off);
-        float4 ami = *reinterpret_cast<float4*>(accA_mi + off);
-        const float4 zmt = *reinterpret_cast<const float4*>(s_dzmt + off);
-        const float4 zmi = *reinterpret_cast<const float4*>(s_dzmi + off);
-        const float zm[4] = {zmt.x, zmt.y, zmt.z, zmt.w}, zi[4] = {zmi.x, zmi.y, zmi.z, zmi.w};
-        float* amtp = reinterpret_cast<float*>(&amt);
-        float* amip = reinterpret_cast<float*>(&ami);
-        float4 gmt4 = make_float4(0.f, 0.f, 0.f, 0.f), gmi4 = gmt4, Gmt = gmt4, Gmi = gmt4;
-        if (FULL) {
-          gmt4 = *reinterpret_cast<const float4*>(s_gmt + off);
-          gmi4 = *reinterpret_cast<const float4*>(s_gmi + off);
-          Gmt = *reinterpret_cast<float4*>(accG_mt + off);
-          Gmi = *reinterpret_cast<float4*>(accG_mi + off);
-        }
-        const float gm[4] = {gmt4.x, gmt4.y, gmt4.z, gmt4.w}, gi[4] = {gmi4.x, gmi4.y, gmi4.z, gmi4.w};
-        float* Gmtp = reinterpret_cast<float*>(&Gmt);
-        float* Gmip = reinterpret_cast<float*>(&Gmi);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = 4 * j + k;
-          const float dze = det.v[i], dzi = FULL ? dei.v[i] : 0.f;
-          amtp[k] += e0 * dze + e1 * dzi;
-          amip[k] += e2 * dze + e3 * dzi;
-          if (FULL) {
-            Gmtp[k] += (ds0 * xet.v[i] + ds1 * xei.v[i]) * invD;
-            Gmip[k] += (ds2 * xet.v[i] + ds3 * xei.v[i]) * invD;
-          }
-          det.v[i] = dze + (e0 * zm[k] + e2 * zi[k]) * invC + (ds0 * gm[k] + ds2 * gi[k]) * invD;
-          dei.v[i] = dzi + (e1 * zm[k] + e3 * zi[k]) * invC + (ds1 * gm[k] + ds3 * gi[k]) * invD;
-        }
-        *reinterpret_cast<float4*>(accA_mt + off) = amt;
-        *reinterpret_cast<float4*>(accA_mi + off) = ami;
-        if (FULL) {
-          *reinterpret_cast<float4*>(accG_mt + off) = Gmt;
-          *reinterpret_cast<float4*>(accG_mi + off) = Gmi;
-        }
-      }
       const long long r_et = 2 * B + r, r_ei = 2 * B + BC + r;      // rows in the [mt; mi; et; ei] layout
-      if (ln) {
-        RowT<D> h;
-        row_load<D>(h, a.x_et + r * D, lane);
-        row_ln_gelu_bwd<D>(h, det, s_gamma, s_beta, p0, p1, lane);
-        row_accum_smem<D>(det, p2, lane);
-        row_load<D>(h, a.x_ei + r * D, lane);
-        row_ln_gelu_bwd<D>(h, dei, s_gamma, s_beta, p0, p1, lane);
-        row_accum_smem<D>(dei, p2, lane);
-      } else {
-        row_accum_smem<D>(det, p0, lane);       // db_et
-        row_accum_smem<D>(dei, p1, lane);       // db_ei
+      float pd0, pd2, q0, q2, pd1, pd3, q1, q3;
+      layer_bwd_row<D, FULL>(a.x_et + r * D, dz_et + r * D, ln, s_gamma, s_beta, s_xmt, s_xmi, s_dzmt, s_dzmi, s_gmt,
+                             s_gmi, e0, e2, ds0, ds2, invC, invD, accA_mt, accA_mi, accG_mt, accG_mi, p0, p1, p2, p0,
+                             a.dcand_hi + r_et * D, a.dcand_lo ? a.dcand_lo + r_et * D : nullptr, lane, pd0, pd2, q0, q2);
+      layer_bwd_row<D, FULL>(a.x_ei + r * D, FULL ? dz_ei + r * D : nullptr, ln, s_gamma, s_beta, s_xmt, s_xmi, s_dzmt,
+                             s_dzmi, s_gmt, s_gmi, e1, e3, ds1, ds3, invC, invD, accA_mt, accA_mi, accG_mt, accG_mi, p0,
+                             p1, p2, p1, a.dcand_hi + r_ei * D, a.dcand_lo ? a.dcand_lo + r_ei * D : nullptr, lane, pd1,
+                             pd3, q1, q3);
+      if (a.dedges_in) {
+        pd0 = warp_sum(pd0); pd1 = warp_sum(pd1); pd2 = warp_sum(pd2); pd3 = warp_sum(pd3);
+        q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
+        if (lane == 0) {
+          a.dedges_in[r] = (pd0 * invC + q0 + ds0) * a.en[0];
+          a.dedges_in[BC + r] = (pd1 * invC + q1 + ds1) * a.en[1];
+          a.dedges_in[2 * BC + r] = (pd2 * invC + q2 + ds2) * a.en[2];
+          a.dedges_in[3 * BC + r] = (pd3 * invC + q3 + ds3) * a.en[3];
+        }
       }
-      row_store_planes<D>(det, a.dcand_hi + r_et * D, a.dcand_lo ? a.dcand_lo + r_et * D : nullptr, lane);
-      row_store_planes<D>(dei, a.dcand_hi + r_ei * D, a.dcand_lo ? a.dcand_lo + r_ei * D : nullptr, lane);
     }
-    if (lane == 0) {
-      s_db[0][warp] = dbeta_mt;
-      s_db[1][warp] = dbeta_mi;
+    if (FULL && lane == 0) {
+      s_db[warp] = dbeta_mt;
+      s_db[NW + warp] = dbeta_mi;
     }
     __syncthreads();
     // mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
     for (int i = tid; i < 2 * D; i += NW * 32) {
       const int which = i / D, col = i - which * D;
-      float t = which ? s_dzmi[col] : s_dzmt[col];
+      float t = which ? (FULL ? s_dzmi[col] : 0.f) : s_dzmt[col];
 #pragma unroll
       for (int w = 0; w < NW; ++w) t += s_acc[(which * NW + w) * D + col];
       a.dxm[(which ? B + b : (long long)b) * D + col] = t;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_bwd_kernel(const LayerBwdAr
     if (FULL && tid < 2) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) t += s_db[tid][w];
+      for (int w = 0; w < NW; ++w) t += s_db[tid * NW + w];
       a.dbeta[tid ? B + b : (long long)b] = t;
     }
   }
@@ -355,11 +356,12 @@ int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
-  const size_t smem = (size_t)(8 + 7 * BW_NW) * D * sizeof(float);
   if (a.full) {
+    const size_t smem = (size_t)(8 + 7 * BW_NW) * D * sizeof(float) + 2 * BW_NW * sizeof(float);
     DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gcn_layer_bwd_kernel<D, BW_NW, true><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
   } else {
+    const size_t smem = (size_t)(5 + 5 * BW_NW) * D * sizeof(float);
     DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gcn_layer_bwd_kernel<D, BW_NW, false><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
   }
@@ -475,25 +477,37 @@ int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const
 // ---------------------------------------------------------------------------------------------
 // colsum_reduce: out_v[col] = sum over sources and CTAs of partials[(cta * nvec + v) * D + col]
 // ---------------------------------------------------------------------------------------------
-__global__ void colsum_reduce_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int ctas, int nvec,
-                                     int D, float* out0, float* out1, float* out2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nvec * D) return;
-  const int v = i / D, col = i - v * D;
-  float* out = v == 0 ? out0 : (v == 1 ? out1 : out2);
-  if (!out) return;
+// block = 32 columns x 8 CTA-slices; slice s sums partial rows s, s+8, ... then a fixed-order smem reduce
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+                                                            int ctas, int nvec, int D, float* out0, float* out1,
+                                                            float* out2) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;                  // flat (v, col)
   float t = 0.f;
-  for (int c = 0; c < ctas; ++c) t += src0[((long long)c * nvec + v) * D + col];
-  if (src1)
-    for (int c = 0; c < ctas; ++c) t += src1[((long long)c * nvec + v) * D + col];
-  out[col] = t;
+  if (i < nvec * D) {
+    const int v = i / D, col = i - v * D;
+    for (int c = slice; c < ctas; c += 8) t += src0[((long long)c * nvec + v) * D + col];
+    if (src1)
+      for (int c = slice; c < ctas; c += 8) t += src1[((long long)c * nvec + v) * D + col];
+  }
+  red[slice][lane] = t;
+  __syncthreads();
+  if (slice == 0 && i < nvec * D) {
+    float r = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) r += red[s2][lane];
+    const int v = i / D, col = i - v * D;
+    float* out = v == 0 ? out0 : (v == 1 ? out1 : out2);
+    if (out) out[col] = r;
+  }
 }
 
 int colsum_reduce(cudaStream_t stream, const float* src0, const float* src1, int nvec, int D, float* out0, float* out1,
                   float* out2) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   const int n = nvec * D;
-  colsum_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(src0, src1, BW_CTAS, nvec, D, out0, out1, out2);
+  colsum_reduce_kernel<<<(n + 31) / 32, 256, 0, stream>>>(src0, src1, BW_CTAS, nvec, D, out0, out1, out2);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }

@@ -25,8 +25,46 @@ namespace drin {
 // ---------------------------------------------------------------------------------------------
 // gcn_layer_fwd
 // ---------------------------------------------------------------------------------------------
+// process one candidate vertex row: returns nothing, updates the per-warp message slices in smem,
+// writes z = x + message as planes and returns the two edge-update dot products (FULL).
+template <int D, bool FULL>
+__device__ __forceinline__ void layer_fwd_row(const float* __restrict__ xrow, bool ln, const float* s_gamma,
+                                              const float* s_beta, const float* s_mt, const float* s_mi,
+                                              const float* s_gmt, const float* s_gmi, float e_mt, float e_mi,
+                                              float* acc_mt, float* acc_mi, bool write_z, bf16* z_hi, bf16* z_lo,
+                                              int lane, float& dot_mt, float& dot_mi) {
+  RowT<D> x;
+  row_load<D>(x, xrow, lane);
+  if (ln) row_ln_gelu<D>(x, s_gamma, s_beta, lane);
+  if (FULL) {
+    dot_mt = row_dot<D>(x, s_gmt, lane);
+    dot_mi = row_dot<D>(x, s_gmi, lane);
+  }
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    float4 am = *reinterpret_cast<float4*>(acc_mt + off);
+    am.x += e_mt * x.v[4 * j]; am.y += e_mt * x.v[4 * j + 1]; am.z += e_mt * x.v[4 * j + 2]; am.w += e_mt * x.v[4 * j + 3];
+    *reinterpret_cast<float4*>(acc_mt + off) = am;
+    if (FULL) {
+      float4 ai = *reinterpret_cast<float4*>(acc_mi + off);
+      ai.x += e_mi * x.v[4 * j]; ai.y += e_mi * x.v[4 * j + 1]; ai.z += e_mi * x.v[4 * j + 2]; ai.w += e_mi * x.v[4 * j + 3];
+      *reinterpret_cast<float4*>(acc_mi + off) = ai;
+    }
+    if (write_z) {
+      const float4 mt = *reinterpret_cast<const float4*>(s_mt + off);
+      const float4 mi = *reinterpret_cast<const float4*>(s_mi + off);
+      x.v[4 * j] += e_mt * mt.x + e_mi * mi.x;
+      x.v[4 * j + 1] += e_mt * mt.y + e_mi * mi.y;
+      x.v[4 * j + 2] += e_mt * mt.z + e_mi * mi.z;
+      x.v[4 * j + 3] += e_mt * mt.w + e_mi * mi.w;
+    }
+  }
+  if (write_z) row_store_planes<D>(x, z_hi, z_lo, lane);
+}
+
 template <int D, int NW, bool FULL>
-__global__ void __launch_bounds__(NW * 32) gcn_layer_fwd_kernel(const LayerFwdArgs a) {
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 2) gcn_layer_fwd_kernel(const LayerFwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* s_mt = sm;                 // [D] mention text vertex (layer input)
   float* s_mi = s_mt + D;           // [D] mention image vertex
@@ -34,7 +72,7 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_fwd_kernel(const LayerFwdAr
   float* s_gmi = s_gmt + D;         // [D]                u = mi   (FULL)
   float* s_gamma = s_gmi + D;       // [D] LayerNorm of the previous layer (if a.ln_gamma)
   float* s_beta = s_gamma + D;      // [D]
-  float* s_acc = s_beta + D;        // [2][NW][D] per-warp partial aggregates
+  float* s_acc = s_beta + D;        // [2][NW][D] per-warp partial messages to the mention vertices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long B = a.B, BC = (long long)a.B * a.C;
   const bool ln = a.ln_gamma != nullptr;
@@ -45,6 +83,8 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_fwd_kernel(const LayerFwdAr
     }
   }
   const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+  float* acc_mt = s_acc + warp * D;
+  float* acc_mi = s_acc + (NW + warp) * D;
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     __syncthreads();                                        // previous mention done with smem
@@ -56,29 +96,31 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_fwd_kernel(const LayerFwdAr
         s_gmi[i] = a.g[(B + b) * D + i];
       }
     }
+#pragma unroll
+    for (int j = 0; j < RowT<D>::NV; ++j) {
+      *reinterpret_cast<float4*>(acc_mt + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(acc_mi + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
     const float beta_mt = FULL ? a.beta_u[b] : 0.f;
     const float beta_mi = FULL ? a.beta_u[B + b] : 0.f;
 
-    RowT<D> amt, ami;                                       // per-warp partial message sums
-#pragma unroll
-    for (int i = 0; i < RowT<D>::NV * 4; ++i) { amt.v[i] = 0.f; ami.v[i] = 0.f; }
-
     for (int c = warp; c < a.C; c += NW) {
       const long long r = (long long)b * a.C + c;
-      RowT<D> xet, xei;
-      row_load<D>(xet, a.x_et + r * D, lane);
-      row_load<D>(xei, a.x_ei + r * D, lane);
-      if (ln) {
-        row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
-        row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
-      }
+      // enable mask (model.py:122); edge order tt (mt-et), ti (mt-ei), it (mi-et), ii (mi-ei)
       const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
       const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      const long long zr_et = (FULL ? 2 * B : B) + r, zr_ei = 2 * B + BC + r;
+      // entity-text row: messages mt <- e0 * et, mi <- e2 * et ; z_et = et + e0 mt + e2 mi (model.py:124-128,139-146)
+      layer_fwd_row<D, FULL>(a.x_et + r * D, ln, s_gamma, s_beta, s_mt, s_mi, s_gmt, s_gmi, e0, e2, acc_mt, acc_mi, true,
+                             a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane, d0, d2);
+      // entity-image row: messages mt <- e1 * ei, mi <- e3 * ei ; z_ei only for full layers
+      layer_fwd_row<D, FULL>(a.x_ei + r * D, ln, s_gamma, s_beta, s_mt, s_mi, s_gmt, s_gmi, e1, e3, acc_mt, acc_mi, FULL,
+                             FULL ? a.z_hi + zr_ei * D : nullptr, (FULL && a.z_lo) ? a.z_lo + zr_ei * D : nullptr, lane,
+                             d1, d3);
       if (FULL) {
-        // dynamic edge update (model.py:131-134,148-153): u in {mt, mi}, v in {et, ei}
-        float d0 = row_dot<D>(xet, s_gmt, lane), d1 = row_dot<D>(xei, s_gmt, lane);
-        float d2 = row_dot<D>(xet, s_gmi, lane), d3 = row_dot<D>(xei, s_gmi, lane);
+        // dynamic edge update (model.py:131-134,148-153): e' = sigmoid((v . g_u + fu . b_v) / D + e)
         d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
         if (lane == 0) {
           a.edges_out[r] = 1.0f / (1.0f + __expf(-((d0 + beta_mt) * invD + e0)));
@@ -87,39 +129,8 @@ __global__ void __launch_bounds__(NW * 32) gcn_layer_fwd_kernel(const LayerFwdAr
           a.edges_out[3 * BC + r] = 1.0f / (1.0f + __expf(-((d3 + beta_mi) * invD + e3)));
         }
       }
-      // messages to the mention vertices (mean over ALL C slots, model.py:144)
-#pragma unroll
-      for (int i = 0; i < RowT<D>::NV * 4; ++i) {
-        amt.v[i] += e0 * xet.v[i] + e1 * xei.v[i];
-        if (FULL) ami.v[i] += e2 * xet.v[i] + e3 * xei.v[i];
-      }
-      // z = x + message for the entity vertices (model.py:146,128)
-      RowT<D> z;
-#pragma unroll
-      for (int j = 0; j < RowT<D>::NV; ++j) {
-        const float4 mt = *reinterpret_cast<const float4*>(s_mt + (j * 32 + lane) * 4);
-        const float4 mi = *reinterpret_cast<const float4*>(s_mi + (j * 32 + lane) * 4);
-        z.v[4 * j] = xet.v[4 * j] + e0 * mt.x + e2 * mi.x;
-        z.v[4 * j + 1] = xet.v[4 * j + 1] + e0 * mt.y + e2 * mi.y;
-        z.v[4 * j + 2] = xet.v[4 * j + 2] + e0 * mt.z + e2 * mi.z;
-        z.v[4 * j + 3] = xet.v[4 * j + 3] + e0 * mt.w + e2 * mi.w;
-        if (FULL) {
-          xei.v[4 * j] += e1 * mt.x + e3 * mi.x;
-          xei.v[4 * j + 1] += e1 * mt.y + e3 * mi.y;
-          xei.v[4 * j + 2] += e1 * mt.z + e3 * mi.z;
-          xei.v[4 * j + 3] += e1 * mt.w + e3 * mi.w;
-        }
-      }
-      const long long zr_et = (FULL ? 2 * B : B) + r;
-      row_store_planes<D>(z, a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane);
-      if (FULL) {
-        const long long zr_ei = 2 * B + BC + r;
-        row_store_planes<D>(xei, a.z_hi + zr_ei * D, a.z_lo ? a.z_lo + zr_ei * D : nullptr, lane);
-      }
     }
-    // cross-warp reduction of the mention messages (fixed order -> deterministic)
-    row_store<D>(amt, s_acc + warp * D, lane);
-    if (FULL) row_store<D>(ami, s_acc + (NW + warp) * D, lane);
+    // cross-warp reduction of the mention messages (fixed order -> deterministic); mean over ALL C slots
     __syncthreads();
     for (int i = tid; i < (FULL ? 2 : 1) * D; i += NW * 32) {
       const int which = i / D, col = i - which * D;
