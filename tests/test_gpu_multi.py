@@ -1,0 +1,24 @@
+"""NCCL data-parallel path on real GPUs (skipped on a single-GPU box): N ranks, each a shard of one global
+batch, reproduce the single-GPU full-batch step.  The CPU/gloo version of the same protocol is
+tests/test_ddp_gloo.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_step_equals_single_gpu_full_batch_step():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "gpu_dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("DPCHECK ")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(line[-1][8:])
+    assert res["loss_err"] < 1e-6 and res["grad_err"] < 1e-5 and res["rank_scores_err"] < 1e-5
