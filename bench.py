@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dataset", default="wikidiverse", choices=["wikidiverse", "wikimel"])
-    ap.add_argument("--batch", type=int, default=0, help="mentions per GPU per step (0: 4096 WikiDiverse, 192 WikiMEL)")
+    ap.add_argument("--batch", type=int, default=0, help="mentions per GPU per step (0: 4096 WikiDiverse, 512 WikiMEL)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -201,7 +201,7 @@ def run_ours(args):
     wm = args.dataset == "wikimel"
     cands = 100 if wm else 10
     Cn = cands + 1
-    B = args.batch or (192 if wm else 4096)
+    B = args.batch or (512 if wm else 4096)
     bf16 = args.precision == "bf16"
     feats = (0, 4, 5, 7, 9, 10)
 

@@ -64,13 +64,24 @@ __device__ __forceinline__ void store_planes(bf16* hi, bf16* lo, long long off, 
 
 static constexpr int FE_MAX_OM = 4;
 
-template <typename T, int NW>
-__global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a) {
+// lane-strided row tile: vector i of the lane covers elements (i*32 + lane)*VN .. +VN-1 (coalesced 512-B requests)
+template <typename T, int NV>
+__device__ __forceinline__ void load_row_tile(const T* __restrict__ row, int lane, float (&f)[NV][Vec<T>::N]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) Vec<T>::load(row + (i * 32 + lane) * Vec<T>::N, f[i]);
+}
+
+// One work item = (mention b, candidate slice).  Slices let WikiMEL-sized mentions (101 candidates x up to
+// 196 KB of entity tokens) spread over several CTAs; slice 0 also owns the mention-side outputs.
+template <typename T, int NW, int D, int R>
+__global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs a) {
   constexpr int VN = Vec<T>::N;
+  constexpr int DV = D / (32 * VN);          // vectors per lane for a D row  (6 fp32 / 3 bf16)
+  constexpr int RV = R / (32 * VN);          // vectors per lane for an R row (16 fp32 / 8 bf16)
   extern __shared__ __align__(16) float sm[];
-  float* s_span = sm;                       // [D]
-  float* s_mo = s_span + a.D;               // [Om][R]
-  float* s_red = s_mo + a.Om * a.R;         // [NW] scratch + results
+  float* s_span = sm;                        // [D]
+  float* s_mo = s_span + D;                  // [Om][R]
+  float* s_red = s_mo + a.Om * R;            // [(1 + Om) * NW] scratch
   __shared__ float s_span_norm;
   __shared__ float s_mo_norm[FE_MAX_OM];
   __shared__ float s_ms[FE_MAX_OM];
@@ -83,8 +94,12 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
   const T* eif = static_cast<const T*>(a.eif);
   const T* eof = static_cast<const T*>(a.eof);
   const long long BC = (long long)a.B * a.C;
+  const int S = a.slices, cps = (a.C + S - 1) / S;
+  const long long items = (long long)a.B * S;
 
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = (int)(item / S), slice = (int)(item - (long long)b * S);
+    const bool owner = slice == 0;
     // ------------------------------ phase A: mention side ------------------------------
     // span mean (ghmfc.py:55-60): rows start..end-1 with Python slice clamping
     long long s = a.start[b], e = a.end[b];
@@ -94,13 +109,24 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
     e = e < 0 ? 0 : (e > a.Lm ? a.Lm : e);
     const float cnt = e > s ? (float)(e - s) : 0.f;          // 0 -> 0/0 = NaN like mean of an empty slice
     float nrm_part = 0.f;
-    for (int v = tid; v < a.D / VN; v += NW * 32) {
+    for (int v = tid; v < D / VN; v += NW * 32) {
       float acc[VN];
 #pragma unroll
       for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-      for (long long r = s; r < e; ++r) {
+      const T* base = mtf + (long long)b * a.Lm * D + v * VN;
+      long long r = s;
+      for (; r + 4 <= e; r += 4) {
+        float f[4][VN];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Vec<T>::load(base + (r + j) * D, f[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] += f[j][i];
+      }
+      for (; r < e; ++r) {
         float f[VN];
-        Vec<T>::load(mtf + ((long long)b * a.Lm + r) * a.D + v * VN, f);
+        Vec<T>::load(base + r * D, f);
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[i] += f[i];
       }
@@ -110,61 +136,63 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
         s_span[v * VN + i] = acc[i];
         nrm_part += acc[i] * acc[i];
       }
-      if (a.span_hi) store_planes<VN>(a.span_hi, a.span_lo, (long long)b * a.D + v * VN, acc);
-      if (a.span_f) {
+      if (owner && a.span_hi) store_planes<VN>(a.span_hi, a.span_lo, (long long)b * D + v * VN, acc);
+      if (owner && a.span_f) {
 #pragma unroll
-        for (int i = 0; i < VN; ++i) a.span_f[(long long)b * a.D + v * VN + i] = acc[i];
+        for (int i = 0; i < VN; ++i) a.span_f[(long long)b * D + v * VN + i] = acc[i];
       }
     }
     nrm_part = warp_sum(nrm_part);
     if (lane == 0) s_red[warp] = nrm_part;
 
-    // region mean (model.py:41): P rows of R
-    for (int v = tid; v < a.R / VN; v += NW * 32) {
-      float acc[VN];
-#pragma unroll
-      for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-      const T* base = mif + (long long)b * a.P * a.R + v * VN;
-      int r = 0;
-      for (; r + 7 <= a.P; r += 7) {                      // 7 independent 16-B loads in flight per thread
-        float f[7][VN];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) Vec<T>::load(base + (long long)(r + j) * a.R, f[j]);
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-#pragma unroll
-          for (int i = 0; i < VN; ++i) acc[i] += f[j][i];
-      }
-      for (; r < a.P; ++r) {
-        float f[VN];
-        Vec<T>::load(base + (long long)r * a.R, f);
-#pragma unroll
-        for (int i = 0; i < VN; ++i) acc[i] += f[i];
-      }
-      const float inv = 1.0f / (float)a.P;
-#pragma unroll
-      for (int i = 0; i < VN; ++i) acc[i] *= inv;
-      if (a.mim_hi) store_planes<VN>(a.mim_hi, a.mim_lo, (long long)b * a.R + v * VN, acc);
-      if (a.mim_f) {
-#pragma unroll
-        for (int i = 0; i < VN; ++i) a.mim_f[(long long)b * a.R + v * VN + i] = acc[i];
-      }
-    }
-
     // mention object crops (model.py:78-79; the singleton dim is already folded) -> smem + norms
     for (int o = 0; o < a.Om; ++o) {
       float part = 0.f;
-      for (int v = tid; v < a.R / VN; v += NW * 32) {
+      for (int v = tid; v < R / VN; v += NW * 32) {
         float f[VN];
-        Vec<T>::load(mof + ((long long)b * a.Om + o) * a.R + v * VN, f);
+        Vec<T>::load(mof + ((long long)b * a.Om + o) * R + v * VN, f);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          s_mo[o * a.R + v * VN + i] = f[i];
+          s_mo[o * R + v * VN + i] = f[i];
           part += f[i] * f[i];
         }
       }
       part = warp_sum(part);
       if (lane == 0) s_red[NW * (1 + o) + warp] = part;
+    }
+
+    // region mean (model.py:41): P rows of R, 7 independent 16-B loads in flight per thread
+    if (owner) {
+      for (int v = tid; v < R / VN; v += NW * 32) {
+        float acc[VN];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+        const T* base = mif + (long long)b * a.P * R + v * VN;
+        int r = 0;
+        for (; r + 7 <= a.P; r += 7) {
+          float f[7][VN];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) Vec<T>::load(base + (long long)(r + j) * R, f[j]);
+#pragma unroll
+          for (int j = 0; j < 7; ++j)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[i] += f[j][i];
+        }
+        for (; r < a.P; ++r) {
+          float f[VN];
+          Vec<T>::load(base + (long long)r * R, f);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] += f[i];
+        }
+        const float inv = 1.0f / (float)a.P;
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] *= inv;
+        if (a.mim_hi) store_planes<VN>(a.mim_hi, a.mim_lo, (long long)b * R + v * VN, acc);
+        if (a.mim_f) {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) a.mim_f[(long long)b * R + v * VN + i] = acc[i];
+        }
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -182,23 +210,33 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
     __syncthreads();
 
     // ------------------------------ phase B: one warp per candidate ------------------------------
-    for (int c = warp; c < a.C; c += NW) {
+    const int c_end = min(a.C, (slice + 1) * cps);
+    for (int c = slice * cps + warp; c < c_end; c += NW) {
       const long long r = (long long)b * a.C + c;
+      // all rows of the candidate that do not depend on anything are requested up front
+      float eo[RV][VN], ec[DV][VN];
+      load_row_tile<T, RV>(eof + r * a.Oe * R, lane, eo);                       // first entity object crop
+      load_row_tile<T, DV>(etf + (a.Le ? r * (long long)a.Le * D : r * D), lane, ec);   // CLS row / pooled row
+
       // --- entity text: tt = cos(span, CLS) and the pooled vertex feature (ghmfc.py:237-249, model.py:73-76)
       float dot = 0.f, nrm = 0.f;
-      if (a.Le == 0) {
-        for (int v = lane; v < a.D / VN; v += 32) {
-          float f[VN];
-          Vec<T>::load(etf + r * a.D + v * VN, f);
 #pragma unroll
-          for (int i = 0; i < VN; ++i) {
-            dot += f[i] * s_span[v * VN + i];
-            nrm += f[i] * f[i];
-          }
-          if (a.ep_hi) store_planes<VN>(a.ep_hi, a.ep_lo, r * a.D + v * VN, f);
+      for (int v = 0; v < DV; ++v) {
+        const float* sp = s_span + (v * 32 + lane) * VN;
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          dot += ec[v][i] * sp[i];
+          nrm += ec[v][i] * ec[v][i];
+        }
+      }
+      if (a.Le == 0) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v) {
+          const long long off = r * D + (v * 32 + lane) * VN;
+          if (a.ep_hi) store_planes<VN>(a.ep_hi, a.ep_lo, off, ec[v]);
           if (a.ep_f) {
 #pragma unroll
-            for (int i = 0; i < VN; ++i) a.ep_f[r * a.D + v * VN + i] = f[i];
+            for (int i = 0; i < VN; ++i) a.ep_f[off + i] = ec[v][i];
           }
         }
       } else {
@@ -210,38 +248,41 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
         if (t1 < 0) t1 += a.Le;                             // Python slice semantics for a negative stop
         if (t1 > a.Le) t1 = a.Le;
         const float cnt_e = t1 > t0 ? (float)(t1 - t0) : 0.f;
-        const T* rowbase = etf + r * (long long)a.Le * a.D;
-        for (int v = lane; v < a.D / VN; v += 32) {
-          float f[VN], acc[VN];
-          Vec<T>::load(rowbase + v * VN, f);                // CLS row
+        const T* rowbase = etf + r * (long long)a.Le * D;
+        float acc[DV][VN];
 #pragma unroll
-          for (int i = 0; i < VN; ++i) {
-            dot += f[i] * s_span[v * VN + i];
-            nrm += f[i] * f[i];
-            acc[i] = 0.f;
-          }
-          long long t = t0;
-          for (; t + 4 <= t1; t += 4) {
-            float g[4][VN];
+        for (int v = 0; v < DV; ++v)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Vec<T>::load(rowbase + (t + j) * a.D + v * VN, g[j]);
+          for (int i = 0; i < VN; ++i) acc[v][i] = 0.f;
+        long long t = t0;
+        for (; t + 4 <= t1; t += 4) {                       // 4 rows x DV vectors in flight per lane
+          float g[4][DV][VN];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 4; ++j) load_row_tile<T, DV>(rowbase + (t + j) * D, lane, g[j]);
 #pragma unroll
-              for (int i = 0; i < VN; ++i) acc[i] += g[j][i];
-          }
-          for (; t < t1; ++t) {
-            float g[VN];
-            Vec<T>::load(rowbase + t * a.D + v * VN, g);
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < VN; ++i) acc[i] += g[i];
-          }
+            for (int v = 0; v < DV; ++v)
 #pragma unroll
-          for (int i = 0; i < VN; ++i) acc[i] = acc[i] / cnt_e;
-          if (a.ep_hi) store_planes<VN>(a.ep_hi, a.ep_lo, r * a.D + v * VN, acc);
+              for (int i = 0; i < VN; ++i) acc[v][i] += g[j][v][i];
+        }
+        for (; t < t1; ++t) {
+          float g[DV][VN];
+          load_row_tile<T, DV>(rowbase + t * D, lane, g);
+#pragma unroll
+          for (int v = 0; v < DV; ++v)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[v][i] += g[v][i];
+        }
+#pragma unroll
+        for (int v = 0; v < DV; ++v) {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[v][i] = acc[v][i] / cnt_e;
+          const long long off = r * D + (v * 32 + lane) * VN;
+          if (a.ep_hi) store_planes<VN>(a.ep_hi, a.ep_lo, off, acc[v]);
           if (a.ep_f) {
 #pragma unroll
-            for (int i = 0; i < VN; ++i) a.ep_f[r * a.D + v * VN + i] = acc[i];
+            for (int i = 0; i < VN; ++i) a.ep_f[off + i] = acc[v][i];
           }
         }
       }
@@ -252,18 +293,19 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
       // --- object crops: ii (model.py:84-92)
       float sim = 0.f, den = 0.f;
       for (int j = 0; j < a.Oe; ++j) {
+        if (j > 0) load_row_tile<T, RV>(eof + (r * a.Oe + j) * R, lane, eo);
         float d[FE_MAX_OM] = {0.f, 0.f, 0.f, 0.f};
         float en2 = 0.f;
-        for (int v = lane; v < a.R / VN; v += 32) {
-          float f[VN];
-          Vec<T>::load(eof + (r * a.Oe + j) * a.R + v * VN, f);
 #pragma unroll
-          for (int i = 0; i < VN; ++i) en2 += f[i] * f[i];
+        for (int v = 0; v < RV; ++v) {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) en2 += eo[v][i] * eo[v][i];
 #pragma unroll
           for (int o = 0; o < FE_MAX_OM; ++o)
             if (o < a.Om) {
+              const float* mo = s_mo + o * R + (v * 32 + lane) * VN;
 #pragma unroll
-              for (int i = 0; i < VN; ++i) d[o] += f[i] * s_mo[o * a.R + v * VN + i];
+              for (int i = 0; i < VN; ++i) d[o] += eo[v][i] * mo[i];
             }
         }
         en2 = warp_sum(en2);
@@ -280,11 +322,9 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
 
       // --- entity image row -> planes (A operand of the entity-image projection, model.py:45)
       if (a.ei_hi) {
-        for (int v = lane; v < a.R / VN; v += 32) {
-          float f[VN];
-          Vec<T>::load(eif + r * a.R + v * VN, f);
-          store_planes<VN>(a.ei_hi, a.ei_lo, r * a.R + v * VN, f);
-        }
+        load_row_tile<T, RV>(eif + r * R, lane, eo);
+#pragma unroll
+        for (int v = 0; v < RV; ++v) store_planes<VN>(a.ei_hi, a.ei_lo, r * R + (v * 32 + lane) * VN, eo[v]);
       }
       if (lane == 0 && a.edges) {                            // model.py:201-204 order tt, ti, it, ii
         a.edges[r] = tt;
@@ -293,35 +333,42 @@ __global__ void __launch_bounds__(NW * 32) frontend_kernel(const FrontendArgs a)
         a.edges[3 * BC + r] = ii;
       }
     }
-    __syncthreads();   // smem is reused by the next mention
+    __syncthreads();   // smem is reused by the next work item
   }
 }
 
 template <typename T>
-static int launch_frontend(cudaStream_t stream, const FrontendArgs& a) {
-  const size_t smem = (size_t)(a.D + a.Om * a.R + 8 * (1 + FE_MAX_OM)) * sizeof(float);
-  const int grid = a.B < 148 * 8 ? a.B : 148 * 8;
-  if (a.C < 32) {
-    frontend_kernel<T, 4><<<grid, 128, smem, stream>>>(a);
-  } else {
-    frontend_kernel<T, 8><<<grid, 256, smem, stream>>>(a);
+static int launch_frontend(cudaStream_t stream, FrontendArgs a) {
+  constexpr int D = 768, R = 2048;
+  const size_t smem = (size_t)(D + a.Om * R + 8 * (1 + FE_MAX_OM)) * sizeof(float);
+  // candidate slices: enough work items to fill the machine (3 CTAs/SM) when the batch alone cannot
+  const int target = 148 * 3;
+  int slices = 1;
+  if (a.C >= 32 && a.B < 2 * target) {
+    slices = (2 * target + a.B - 1) / a.B;
+    const int max_slices = (a.C + 7) / 8;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
   }
+  a.slices = slices;
+  const long long items = (long long)a.B * slices;
+  const int grid = (int)(items < 148 * 6 ? items : 148 * 6);
+  frontend_kernel<T, 4, D, R><<<grid, 128, smem, stream>>>(a);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }
 
 int frontend(cudaStream_t stream, const FrontendArgs& a, bool bf16_features) {
   prof::Scope prof_scope(stream, prof::FRONTEND);
-  if (a.D % 256 || a.R % 256) return fail(DRIN_ERR_ARG, "frontend: D and R must be multiples of 256");
+  if (a.D != 768 || a.R != 2048)
+    return fail(DRIN_ERR_ARG, "frontend: built for bert_embed_dim 768 / resnet_embed_dim 2048 (got %d / %d)", a.D, a.R);
   if (a.Om > FE_MAX_OM) return fail(DRIN_ERR_ARG, "frontend: at most %d mention objects", FE_MAX_OM);
   if (a.B <= 0 || a.C <= 0) return fail(DRIN_ERR_ARG, "frontend: empty batch");
   static bool attr_set = false;
   if (!attr_set) {
     const int max_smem = 100 * 1024;
-    DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<bf16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<float, 4, 768, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<bf16, 4, 768, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   return bf16_features ? launch_frontend<bf16>(stream, a) : launch_frontend<float>(stream, a);

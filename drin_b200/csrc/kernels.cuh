@@ -27,6 +27,7 @@ int split_planes(cudaStream_t stream, const float* x, bf16* hi, bf16* lo, long l
 // frontend.cu
 struct FrontendArgs {
   int B, C, Lm, Le, P, Om, Oe, D, R;
+  int slices;                    // candidate slices per mention (set by the launcher)
   const void* mtf; const long long* start; const long long* end;
   const void* mif; const void* mof; const float* mos;
   const void* etf; const long long* emask; const void* eif; const void* eof; const float* eos;
