@@ -81,10 +81,9 @@ __global__ void __launch_bounds__(NW * 32) score_bwd_kernel(const ScoreBwdArgs a
     const float nm = s_mnorm;
     for (int c = warp; c < a.C; c += NW) {
       const long long r = (long long)b * a.C + c;
-      RowT<D> h, e;
+      RowT<D> h, e, de;
       row_load<D>(h, a.h_et + r * D, lane);
-      e = h;
-      row_ln_gelu<D>(e, s_gamma, s_beta, lane);
+      const float rstd = row_ln_gelu_recompute<D>(h, e, de, s_gamma, s_beta, lane);   // h := xhat, e := activated
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < RowT<D>::NV * 4; ++i) q += e.v[i] * e.v[i];
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(NW * 32) score_bwd_kernel(const ScoreBwdArgs a
         e.v[4 * j + 2] = w1 * mv.z - w2 * e.v[4 * j + 2];
         e.v[4 * j + 3] = w1 * mv.w - w2 * e.v[4 * j + 3];
       }
-      row_ln_gelu_bwd<D>(h, e, s_gamma, s_beta, pg, pb, lane);
+      row_ln_gelu_bwd_from<D>(h, de, rstd, e, s_gamma, pg, pb, lane);
       row_accum_smem<D>(e, ph, lane);
       const long long zr = B + r;
       row_store_planes<D>(e, a.dh_hi + zr * D, a.dh_lo ? a.dh_lo + zr * D : nullptr, lane);
@@ -180,7 +179,12 @@ __device__ __forceinline__ void layer_bwd_row(const float* __restrict__ xrow, co
 #pragma unroll
     for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] = 0.f;
   }
-  if (ln) row_ln_gelu<D>(x, s_gamma, s_beta, lane);
+  RowT<D> xhat, dact;                                 // ln: normalised row and gelu'(y), computed once
+  float rstd = 0.f;
+  if (ln) {
+    xhat = x;
+    rstd = row_ln_gelu_recompute<D>(xhat, x, dact, s_gamma, s_beta, lane);   // x becomes the activated row
+  }
   pd_mt = row_dot<D>(x, s_dzmt, lane);
   pd_mi = FULL ? row_dot<D>(x, s_dzmi, lane) : 0.f;
   q_mt = has_dz ? row_dot<D>(d, s_xmt, lane) : 0.f;
@@ -216,8 +220,7 @@ __device__ __forceinline__ void layer_bwd_row(const float* __restrict__ xrow, co
     }
   }
   if (ln) {
-    row_load<D>(x, xrow, lane);                       // pre-LN row again (L1/L2 hit)
-    row_ln_gelu_bwd<D>(x, d, s_gamma, s_beta, p0, p1, lane);
+    row_ln_gelu_bwd_from<D>(xhat, dact, rstd, d, s_gamma, p0, p1, lane);
     row_accum_smem<D>(d, p2, lane);
   } else {
     row_accum_smem<D>(d, pbias, lane);                // first layer: bias gradient of the input projection

@@ -18,6 +18,7 @@
 // Layout: a warp owns one vertex row; lane l holds elements (j*32 + l)*4 .. +3, j < D/128, i.e. every
 // load/store is a fully coalesced 512-B warp transaction.  Row statistics use warp shuffles.
 #include "kernels.cuh"
+#include "pipe.cuh"
 #include "rows.cuh"
 
 namespace drin {
@@ -63,102 +64,198 @@ __device__ __forceinline__ void layer_fwd_row(const float* __restrict__ xrow, bo
   if (write_z) row_store_planes<D>(x, z_hi, z_lo, lane);
 }
 
+// Shared-memory staged version: a producer warp streams each mention's candidate rows (and its four
+// mention-side vectors) into a 2-stage ring with 1-D bulk async copies (TMA engine, mbarrier completion);
+// NW consumer warps process rows out of shared memory.  Bytes in flight are set by the ring (up to ~78 KB
+// per SM), not by registers or occupancy, and the consumers never wait on HBM latency.
+static constexpr int ST_CH = 11;       // candidate rows per array and chunk (one WikiDiverse mention)
+static constexpr int ST_STAGES = 2;
+
 template <int D, int NW, bool FULL>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 2) gcn_layer_fwd_kernel(const LayerFwdArgs a) {
-  extern __shared__ __align__(16) float sm[];
-  float* s_mt = sm;                 // [D] mention text vertex (layer input)
-  float* s_mi = s_mt + D;           // [D] mention image vertex
-  float* s_gmt = s_mi + D;          // [D] g = fu W_v for u = mt   (FULL)
-  float* s_gmi = s_gmt + D;         // [D]                u = mi   (FULL)
-  float* s_gamma = s_gmi + D;       // [D] LayerNorm of the previous layer (if a.ln_gamma)
-  float* s_beta = s_gamma + D;      // [D]
-  float* s_acc = s_beta + D;        // [2][NW][D] per-warp partial messages to the mention vertices
+__global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const LayerFwdArgs a) {
+  extern __shared__ __align__(128) float sm[];
+  constexpr int NVEC = FULL ? 4 : 2;                          // mt, mi (, g_mt, g_mi)
+  constexpr int STAGE_FLOATS = (2 * ST_CH + NVEC) * D;
+  float* s_gamma = sm + ST_STAGES * STAGE_FLOATS;             // LayerNorm of the previous layer (if a.ln_gamma)
+  float* s_beta = s_gamma + D;
+  float* s_acc = s_beta + D;                                  // [2][NW][D] per-warp partial messages
+  __shared__ __align__(8) unsigned long long bars[2 * ST_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long B = a.B, BC = (long long)a.B * a.C;
   const bool ln = a.ln_gamma != nullptr;
+  const int nchunks = (a.C + ST_CH - 1) / ST_CH;
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[ST_STAGES + s]); };
+  if (tid == 0) {
+    for (int s = 0; s < ST_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (ln) {
-    for (int i = tid; i < D; i += NW * 32) {
+    for (int i = tid; i < D; i += (NW + 1) * 32) {
       s_gamma[i] = a.ln_gamma[i];
       s_beta[i] = a.ln_beta[i];
     }
   }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        for (int k = 0; k < nchunks; ++k) {
+          const int n = min(ST_CH, a.C - k * ST_CH);
+          const long long r0 = (long long)b * a.C + k * ST_CH;
+          mbar_wait(empty_bar(stage), phase ^ 1u, nullptr, 0);
+          const uint32_t row_bytes = (uint32_t)(n * D * sizeof(float));
+          mbar_arrive_expect_tx(full_bar(stage), 2 * row_bytes + NVEC * D * (uint32_t)sizeof(float));
+          const uint32_t base = smem_u32(sm + stage * STAGE_FLOATS);
+          bulk_copy_g2s(base, a.x_et + r0 * D, row_bytes, full_bar(stage));
+          bulk_copy_g2s(base + ST_CH * D * 4, a.x_ei + r0 * D, row_bytes, full_bar(stage));
+          const uint32_t vb = base + 2 * ST_CH * D * 4;
+          bulk_copy_g2s(vb, a.xm + (long long)b * D, D * 4, full_bar(stage));
+          bulk_copy_g2s(vb + D * 4, a.xm + (B + b) * D, D * 4, full_bar(stage));
+          if (FULL) {
+            bulk_copy_g2s(vb + 2 * D * 4, a.g + (long long)b * D, D * 4, full_bar(stage));
+            bulk_copy_g2s(vb + 3 * D * 4, a.g + (B + b) * D, D * 4, full_bar(stage));
+          }
+          if (++stage == ST_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
   const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
   float* acc_mt = s_acc + warp * D;
   float* acc_mi = s_acc + (NW + warp) * D;
-
+  int stage = 0;
+  uint32_t phase = 0;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    __syncthreads();                                        // previous mention done with smem
-    for (int i = tid; i < D; i += NW * 32) {
-      s_mt[i] = a.xm[(long long)b * D + i];
-      s_mi[i] = a.xm[(B + b) * D + i];
-      if (FULL) {
-        s_gmt[i] = a.g[(long long)b * D + i];
-        s_gmi[i] = a.g[(B + b) * D + i];
-      }
-    }
 #pragma unroll
     for (int j = 0; j < RowT<D>::NV; ++j) {
       *reinterpret_cast<float4*>(acc_mt + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(acc_mi + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
     const float beta_mt = FULL ? a.beta_u[b] : 0.f;
     const float beta_mi = FULL ? a.beta_u[B + b] : 0.f;
-
-    for (int c = warp; c < a.C; c += NW) {
-      const long long r = (long long)b * a.C + c;
-      // enable mask (model.py:122); edge order tt (mt-et), ti (mt-ei), it (mi-et), ii (mi-ei)
-      const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
-      const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-      const long long zr_et = (FULL ? 2 * B : B) + r, zr_ei = 2 * B + BC + r;
-      // entity-text row: messages mt <- e0 * et, mi <- e2 * et ; z_et = et + e0 mt + e2 mi (model.py:124-128,139-146)
-      layer_fwd_row<D, FULL>(a.x_et + r * D, ln, s_gamma, s_beta, s_mt, s_mi, s_gmt, s_gmi, e0, e2, acc_mt, acc_mi, true,
-                             a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane, d0, d2);
-      // entity-image row: messages mt <- e1 * ei, mi <- e3 * ei ; z_ei only for full layers
-      layer_fwd_row<D, FULL>(a.x_ei + r * D, ln, s_gamma, s_beta, s_mt, s_mi, s_gmt, s_gmi, e1, e3, acc_mt, acc_mi, FULL,
-                             FULL ? a.z_hi + zr_ei * D : nullptr, (FULL && a.z_lo) ? a.z_lo + zr_ei * D : nullptr, lane,
-                             d1, d3);
-      if (FULL) {
-        // dynamic edge update (model.py:131-134,148-153): e' = sigmoid((v . g_u + fu . b_v) / D + e)
-        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
-        if (lane == 0) {
-          a.edges_out[r] = 1.0f / (1.0f + __expf(-((d0 + beta_mt) * invD + e0)));
-          a.edges_out[BC + r] = 1.0f / (1.0f + __expf(-((d1 + beta_mt) * invD + e1)));
-          a.edges_out[2 * BC + r] = 1.0f / (1.0f + __expf(-((d2 + beta_mi) * invD + e2)));
-          a.edges_out[3 * BC + r] = 1.0f / (1.0f + __expf(-((d3 + beta_mi) * invD + e3)));
+    for (int k = 0; k < nchunks; ++k) {
+      const int n = min(ST_CH, a.C - k * ST_CH);
+      mbar_wait(full_bar(stage), phase, nullptr, 0);
+      const float* st = sm + stage * STAGE_FLOATS;
+      const float* rows_et = st;
+      const float* rows_ei = st + ST_CH * D;
+      const float* s_mt = st + 2 * ST_CH * D;
+      const float* s_mi = s_mt + D;
+      const float* s_gmt = s_mi + D;
+      const float* s_gmi = s_gmt + D;
+      for (int c = warp; c < n; c += NW) {
+        const long long r = (long long)b * a.C + k * ST_CH + c;
+        // enable mask (model.py:122); edge order tt (mt-et), ti (mt-ei), it (mi-et), ii (mi-ei)
+        const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
+        const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        const long long zr_et = (FULL ? 2 * B : B) + r, zr_ei = 2 * B + BC + r;
+        // both vertex rows of the candidate are processed together (independent instruction streams -> ILP);
+        // messages: mt <- e0 et + e1 ei, mi <- e2 et + e3 ei ; z_et = et + e0 mt + e2 mi ; z_ei = ei + e1 mt + e3 mi
+        // (model.py:124-128,139-146)
+        RowT<D> xet, xei;
+        row_load<D>(xet, rows_et + c * D, lane);
+        row_load<D>(xei, rows_ei + c * D, lane);
+        if (ln) {
+          row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
+          row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
+        }
+        if (FULL) {
+          d0 = row_dot<D>(xet, s_gmt, lane); d1 = row_dot<D>(xei, s_gmt, lane);
+          d2 = row_dot<D>(xet, s_gmi, lane); d3 = row_dot<D>(xei, s_gmi, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < RowT<D>::NV; ++j) {
+          const int off = (j * 32 + lane) * 4;
+          float4 am = *reinterpret_cast<float4*>(acc_mt + off);
+          am.x += e0 * xet.v[4 * j] + e1 * xei.v[4 * j];
+          am.y += e0 * xet.v[4 * j + 1] + e1 * xei.v[4 * j + 1];
+          am.z += e0 * xet.v[4 * j + 2] + e1 * xei.v[4 * j + 2];
+          am.w += e0 * xet.v[4 * j + 3] + e1 * xei.v[4 * j + 3];
+          *reinterpret_cast<float4*>(acc_mt + off) = am;
+          if (FULL) {
+            float4 ai = *reinterpret_cast<float4*>(acc_mi + off);
+            ai.x += e2 * xet.v[4 * j] + e3 * xei.v[4 * j];
+            ai.y += e2 * xet.v[4 * j + 1] + e3 * xei.v[4 * j + 1];
+            ai.z += e2 * xet.v[4 * j + 2] + e3 * xei.v[4 * j + 2];
+            ai.w += e2 * xet.v[4 * j + 3] + e3 * xei.v[4 * j + 3];
+            *reinterpret_cast<float4*>(acc_mi + off) = ai;
+          }
+          const float4 mt = *reinterpret_cast<const float4*>(s_mt + off);
+          const float4 mi = *reinterpret_cast<const float4*>(s_mi + off);
+          xet.v[4 * j] += e0 * mt.x + e2 * mi.x;
+          xet.v[4 * j + 1] += e0 * mt.y + e2 * mi.y;
+          xet.v[4 * j + 2] += e0 * mt.z + e2 * mi.z;
+          xet.v[4 * j + 3] += e0 * mt.w + e2 * mi.w;
+          if (FULL) {
+            xei.v[4 * j] += e1 * mt.x + e3 * mi.x;
+            xei.v[4 * j + 1] += e1 * mt.y + e3 * mi.y;
+            xei.v[4 * j + 2] += e1 * mt.z + e3 * mi.z;
+            xei.v[4 * j + 3] += e1 * mt.w + e3 * mi.w;
+          }
+        }
+        row_store_planes<D>(xet, a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane);
+        if (FULL) row_store_planes<D>(xei, a.z_hi + zr_ei * D, a.z_lo ? a.z_lo + zr_ei * D : nullptr, lane);
+        if (FULL) {
+          // dynamic edge update (model.py:131-134,148-153): e' = sigmoid((v . g_u + fu . b_v) / D + e)
+          d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
+          if (lane == 0) {
+            a.edges_out[r] = 1.0f / (1.0f + __expf(-((d0 + beta_mt) * invD + e0)));
+            a.edges_out[BC + r] = 1.0f / (1.0f + __expf(-((d1 + beta_mt) * invD + e1)));
+            a.edges_out[2 * BC + r] = 1.0f / (1.0f + __expf(-((d2 + beta_mi) * invD + e2)));
+            a.edges_out[3 * BC + r] = 1.0f / (1.0f + __expf(-((d3 + beta_mi) * invD + e3)));
+          }
         }
       }
-    }
-    // cross-warp reduction of the mention messages (fixed order -> deterministic); mean over ALL C slots
-    __syncthreads();
-    for (int i = tid; i < (FULL ? 2 : 1) * D; i += NW * 32) {
-      const int which = i / D, col = i - which * D;
-      float t = 0.f;
+      if (k == nchunks - 1) {
+        // cross-warp reduction of the mention messages (fixed order -> deterministic); mean over ALL C slots
+        named_bar_sync(1, NW * 32);
+        for (int i = tid; i < (FULL ? 2 : 1) * D; i += NW * 32) {
+          const int which = i / D, col = i - which * D;
+          float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) t += s_acc[(which * NW + w) * D + col];
-      const float zval = (which ? s_mi[col] : s_mt[col]) + t * invC;
-      bf16 h, l;
-      split_bf16(zval, h, l);
-      const long long zr = which ? B + b : b;
-      a.z_hi[zr * D + col] = h;
-      if (a.z_lo) a.z_lo[zr * D + col] = l;
+          for (int w = 0; w < NW; ++w) t += s_acc[(which * NW + w) * D + col];
+          const float zval = (which ? s_mi[col] : s_mt[col]) + t * invC;
+          bf16 h, l;
+          split_bf16(zval, h, l);
+          const long long zr = which ? B + b : b;
+          a.z_hi[zr * D + col] = h;
+          if (a.z_lo) a.z_lo[zr * D + col] = l;
+        }
+        named_bar_sync(1, NW * 32);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (++stage == ST_STAGES) { stage = 0; phase ^= 1u; }
     }
   }
 }
 
 template <int D, int NW>
 static int launch_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
-  const size_t smem = (size_t)(6 * D + 2 * NW * D) * sizeof(float);
-  const int grid = a.B < 148 * 8 ? a.B : 148 * 8;
+  const int nvec = a.full ? 4 : 2;
+  const size_t smem = (size_t)(ST_STAGES * (2 * ST_CH + nvec) * D + 2 * D + 2 * NW * D) * sizeof(float);
+  const int grid = a.B < 148 ? a.B : 148;
   if (a.full) {
     DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_fwd_kernel<D, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    gcn_layer_fwd_kernel<D, NW, true><<<grid, NW * 32, smem, stream>>>(a);
+    gcn_layer_fwd_kernel<D, NW, true><<<grid, (NW + 1) * 32, smem, stream>>>(a);
   } else {
     DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_fwd_kernel<D, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    gcn_layer_fwd_kernel<D, NW, false><<<grid, NW * 32, smem, stream>>>(a);
+    gcn_layer_fwd_kernel<D, NW, false><<<grid, (NW + 1) * 32, smem, stream>>>(a);
   }
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
@@ -167,7 +264,7 @@ static int launch_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
 int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: gcn_embed_dim %d not built (768 only)", a.D);
-  return a.C < 32 ? launch_layer_fwd<768, 4>(stream, a) : launch_layer_fwd<768, 8>(stream, a);
+  return launch_layer_fwd<768, 8>(stream, a);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,18 +27,23 @@ __device__ __forceinline__ void row_store(const RowT<D>& r, float* __restrict__ 
     *reinterpret_cast<float4*>(p + (j * 32 + lane) * 4) =
         make_float4(r.v[4 * j], r.v[4 * j + 1], r.v[4 * j + 2], r.v[4 * j + 3]);
 }
+// (hi, lo) planes of two floats with packed converts: hi2 = cvt.rn.bf16x2(b, a); lo2 = cvt.rn.bf16x2(b - hi_b, a - hi_a)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi2 << 16);
+  const float rb = b - __uint_as_float(hi2 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(rb), "f"(ra));
+}
 template <int D>
 __device__ __forceinline__ void row_store_planes(const RowT<D>& r, bf16* __restrict__ hi, bf16* __restrict__ lo,
                                                  int lane) {
 #pragma unroll
   for (int j = 0; j < RowT<D>::NV; ++j) {
-    bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-    split_bf16(r.v[4 * j], h0, l0);
-    split_bf16(r.v[4 * j + 1], h1, l1);
-    split_bf16(r.v[4 * j + 2], h2, l2);
-    split_bf16(r.v[4 * j + 3], h3, l3);
-    *reinterpret_cast<uint2*>(hi + (j * 32 + lane) * 4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-    if (lo) *reinterpret_cast<uint2*>(lo + (j * 32 + lane) * 4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(r.v[4 * j], r.v[4 * j + 1], h0, l0);
+    split_bf16x2(r.v[4 * j + 2], r.v[4 * j + 3], h1, l1);
+    *reinterpret_cast<uint2*>(hi + (j * 32 + lane) * 4) = make_uint2(h0, h1);
+    if (lo) *reinterpret_cast<uint2*>(lo + (j * 32 + lane) * 4) = make_uint2(l0, l1);
   }
 }
 template <int D>
@@ -140,6 +145,74 @@ __device__ __forceinline__ void row_ln_gelu_bwd(const RowT<D>& h, RowT<D>& d, co
     const float xh = (h.v[i] - mean) * rstd;
     d.v[i] = rstd * (d.v[i] - m1 - xh * m2);
   }
+}
+
+// Forward recompute for the backward kernels, done ONCE per row: h -> xhat (in place), a = gelu(y),
+// da = gelu'(y) with y = gamma * xhat + beta; returns rstd.
+template <int D>
+__device__ __forceinline__ float row_ln_gelu_recompute(RowT<D>& h, RowT<D>& act, RowT<D>& dact,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) s += h.v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) {
+    const float t = h.v[i] - mean;
+    q += t * t;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + off);
+    const float4 b = *reinterpret_cast<const float4*>(beta + off);
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (h.v[4 * j + k] - mean) * rstd;
+      h.v[4 * j + k] = xh;
+      gelu_both(fmaf(xh, gg[k], bb[k]), act.v[4 * j + k], dact.v[4 * j + k]);
+    }
+  }
+  return rstd;
+}
+
+// LayerNorm+GELU backward from the recomputed pieces: on entry d = dL/da, on exit dL/dh.
+template <int D>
+__device__ __forceinline__ void row_ln_gelu_bwd_from(const RowT<D>& xhat, const RowT<D>& dact, float rstd, RowT<D>& d,
+                                                     const float* __restrict__ gamma, float* __restrict__ pg,
+                                                     float* __restrict__ pb, int lane) {
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < RowT<D>::NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + off);
+    const float gg[4] = {g.x, g.y, g.z, g.w};
+    float4 ag = *reinterpret_cast<float4*>(pg + off);
+    float4 ab = *reinterpret_cast<float4*>(pb + off);
+    float* agp = reinterpret_cast<float*>(&ag);
+    float* abp = reinterpret_cast<float*>(&ab);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = xhat.v[4 * j + k];
+      const float dy = d.v[4 * j + k] * dact.v[4 * j + k];
+      agp[k] += dy * xh;
+      abp[k] += dy;
+      const float dxh = dy * gg[k];
+      d.v[4 * j + k] = dxh;
+      m1 += dxh;
+      m2 += dxh * xh;
+    }
+    *reinterpret_cast<float4*>(pg + off) = ag;
+    *reinterpret_cast<float4*>(pb + off) = ab;
+  }
+  m1 = warp_sum(m1) * (1.0f / D);
+  m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+  for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] = rstd * (d.v[i] - m1 - xhat.v[i] * m2);
 }
 
 }  // namespace drin
