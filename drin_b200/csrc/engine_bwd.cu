@@ -55,7 +55,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       sa.h_mt = lw.h; sa.h_et = lw.h + B * D; sa.gamma = lp.ln_w; sa.beta = lp.ln_b; sa.dscores = dscores;
       sa.dh_hi = ws.dh.hi; sa.dh_lo = ws.dh.lo; sa.partials = partA;
       DRIN_TRY(score_bwd(stream, sa));
-      DRIN_TRY(colsum_reduce(stream, partA, nullptr, 3, D, lg.ln_w, lg.ln_b, lg.b_h));
+      DRIN_TRY(colsum_reduce(stream, partA, backward_ctas(), nullptr, 0, 3, D, lg.ln_w, lg.ln_b, lg.b_h));
     }
     // dZ = dH W_h ; dW_h = dH^T Z
     {
@@ -102,7 +102,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       ef.C = ws.dfu; ef.ldc = D;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.dg_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, ef));
       DRIN_TRY(dfu_finish(stream, D, ws.dfu, ws.dbeta, lp.b_v, lw.fu, 2 * B, ws.dfu_p.hi, ws.dfu_p.lo, partB));
-      DRIN_TRY(colsum_reduce(stream, partB, nullptr, 2, D, lg.b_u, lg.b_v, nullptr));
+      DRIN_TRY(colsum_reduce(stream, partB, backward_ctas(), nullptr, 0, 2, D, lg.b_u, lg.b_v, nullptr));
       DRIN_TRY(weight_grad(stream, ws, op(lw.fu_p, 2 * B, D), op(ws.dg_p, 2 * B, D), D, D, 2 * B, lg.w_v));
       DRIN_TRY(weight_grad(stream, ws, op(ws.dfu_p, 2 * B, D), op(lw.xm_p, 2 * B, D), D, D, 2 * B, lg.w_u));
       GemmEpilogue ex;
@@ -125,10 +125,10 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     DRIN_TRY(mention_bwd_finish(stream, ma));
     if (l > 0) {
       const drin_layer_params& pg = grads.layer[l - 1];
-      DRIN_TRY(colsum_reduce(stream, partA, partB, 3, D, pg.ln_w, pg.ln_b, pg.b_h));
+      DRIN_TRY(colsum_reduce(stream, partA, layer_bwd_ctas(), partB, backward_ctas(), 3, D, pg.ln_w, pg.ln_b, pg.b_h));
     } else {
-      DRIN_TRY(colsum_reduce(stream, partA, nullptr, 3, D, grads.b_et, grads.b_ei, nullptr));
-      DRIN_TRY(colsum_reduce(stream, partB, nullptr, 3, D, grads.b_mt, grads.b_mi, nullptr));
+      DRIN_TRY(colsum_reduce(stream, partA, layer_bwd_ctas(), nullptr, 0, 3, D, grads.b_et, grads.b_ei, nullptr));
+      DRIN_TRY(colsum_reduce(stream, partB, backward_ctas(), nullptr, 0, 3, D, grads.b_mt, grads.b_mi, nullptr));
     }
   }
 

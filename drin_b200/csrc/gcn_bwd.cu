@@ -12,7 +12,10 @@
 //
 // Partial sums live in per-warp shared-memory slices and are reduced in a fixed order, so gradients are
 // bit-reproducible run to run.
+#include <stdlib.h>
+
 #include "kernels.cuh"
+#include "pipe.cuh"
 #include "rows.cuh"
 
 namespace drin {
@@ -355,10 +358,351 @@ __global__ void __launch_bounds__(NW * 32, FULL ? 2 : 3) gcn_layer_bwd_kernel(co
   flush_partials<D, NW>(s_part, 3, a.partials, tid);
 }
 
+// ---------------------------------------------------------------------------------------------
+// gcn_layer_bwd, shared-memory staged version (default)
+// ---------------------------------------------------------------------------------------------
+// A producer warp streams chunks of BS_CH candidates (vertex rows + their dz rows + the mention-side
+// vectors) into a 2-stage ring with bulk async copies; BS_NW consumer warps alternate between
+//   column phases : thread t owns columns t and t + 384; all sums over candidates (messages to the mention
+//                   vertices, g gradients, bias / LayerNorm parameter gradients) are accumulated in REGISTERS in
+//                   candidate order -> no per-warp shared-memory slices, deterministic, and
+//   a row phase   : one warp per vertex row (LayerNorm/GELU recompute, edge-gradient dot products, dL/dx,
+//                   LayerNorm backward, gradient planes), which leaves xhat / dy (or dL/dx) in the ring for the
+//                   second column phase.
+// HBM latency is hidden by the ring, and the small per-warp state allows 12 consumer warps per SM.
+static constexpr int BS_NW = 12;
+static constexpr int BS_CH = 6;
+static constexpr int BS_CONS = BS_NW * 32;            // 384 consumer threads = D / 2
+static constexpr int BS_THREADS = BS_CONS + 32;
+static constexpr int BS_STAGES = 2;
+static constexpr int BS_GRID = 148;                   // one persistent CTA per SM
+
+template <int D, bool FULL>
+__global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(const LayerBwdArgs a) {
+  static_assert(D == 2 * BS_CONS, "column ownership assumes D = 2 * consumer threads");
+  extern __shared__ __align__(128) float sm[];
+  constexpr int STAGE_FLOATS = (4 * BS_CH + 6) * D;
+  float* s_gamma = sm + BS_STAGES * STAGE_FLOATS;
+  float* s_beta = s_gamma + D;
+  float* s_sc = s_beta + D;                            // [2][CH][8]  e0..e3, ds0..ds3
+  float* s_dots = s_sc + 2 * BS_CH * 8;                // [CH][2][4]  pd_mt, pd_mi, q_mt, q_mi per row
+  float* s_stat = s_dots + BS_CH * 8;                  // [CH][2][4]  rstd, m1, m2
+  __shared__ __align__(8) unsigned long long bars[2 * BS_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long B = a.B, BC = (long long)a.B * a.C;
+  const bool ln = a.ln_gamma != nullptr;
+  const int nchunks = (a.C + BS_CH - 1) / BS_CH;
+  auto full_bar = [&](int st) { return smem_u32(&bars[st]); };
+  auto empty_bar = [&](int st) { return smem_u32(&bars[BS_STAGES + st]); };
+  if (tid == 0) {
+    for (int st = 0; st < BS_STAGES; ++st) {
+      mbar_init(full_bar(st), 1);
+      mbar_init(empty_bar(st), BS_NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (ln) {
+    for (int i = tid; i < D; i += BS_THREADS) {
+      s_gamma[i] = a.ln_gamma[i];
+      s_beta[i] = a.ln_beta[i];
+    }
+  }
+  __syncthreads();
+  const float* dz_mt = a.dz;
+  const float* dz_mi = FULL ? a.dz + B * D : nullptr;
+  const float* dz_et = a.dz + (FULL ? 2 * B : B) * D;
+  const float* dz_ei = FULL ? a.dz + (2 * B + BC) * D : nullptr;
+
+  if (warp == BS_NW) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        for (int k = 0; k < nchunks; ++k) {
+          const int n = min(BS_CH, a.C - k * BS_CH);
+          const long long r0 = (long long)b * a.C + k * BS_CH;
+          mbar_wait(empty_bar(stage), phase ^ 1u, nullptr, 0);
+          const uint32_t rb = (uint32_t)(n * D * sizeof(float)), vb = D * (uint32_t)sizeof(float);
+          mbar_arrive_expect_tx(full_bar(stage), (FULL ? 4u : 3u) * rb + (FULL ? 6u : 3u) * vb);
+          const uint32_t base = smem_u32(sm + stage * STAGE_FLOATS);
+          const uint32_t arr = BS_CH * D * 4;
+          bulk_copy_g2s(base, a.x_et + r0 * D, rb, full_bar(stage));
+          bulk_copy_g2s(base + arr, a.x_ei + r0 * D, rb, full_bar(stage));
+          bulk_copy_g2s(base + 2 * arr, dz_et + r0 * D, rb, full_bar(stage));
+          if (FULL) bulk_copy_g2s(base + 3 * arr, dz_ei + r0 * D, rb, full_bar(stage));
+          const uint32_t v0 = base + 4 * arr;
+          bulk_copy_g2s(v0, a.xm + (long long)b * D, vb, full_bar(stage));
+          bulk_copy_g2s(v0 + vb, a.xm + (B + b) * D, vb, full_bar(stage));
+          bulk_copy_g2s(v0 + 2 * vb, dz_mt + (long long)b * D, vb, full_bar(stage));
+          if (FULL) {
+            bulk_copy_g2s(v0 + 3 * vb, dz_mi + (long long)b * D, vb, full_bar(stage));
+            bulk_copy_g2s(v0 + 4 * vb, a.g + (long long)b * D, vb, full_bar(stage));
+            bulk_copy_g2s(v0 + 5 * vb, a.g + (B + b) * D, vb, full_bar(stage));
+          }
+          if (++stage == BS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+  const int col0 = tid, col1 = tid + BS_CONS;
+  float part[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // per-thread column partial sums for the whole kernel
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    float A_mt[2] = {0.f, 0.f}, A_mi[2] = {0.f, 0.f}, G_mt[2] = {0.f, 0.f}, G_mi[2] = {0.f, 0.f};
+    float dbeta_mt = 0.f, dbeta_mi = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      const int n = min(BS_CH, a.C - k * BS_CH);
+      const long long r0 = (long long)b * a.C + k * BS_CH;
+      float* st = sm + stage * STAGE_FLOATS;
+      float* Xet = st;
+      float* Xei = st + BS_CH * D;
+      float* DZet = st + 2 * BS_CH * D;
+      float* DZei = st + 3 * BS_CH * D;                  // full: dz of the entity-image rows; else scratch
+      const float* s_xmt = st + 4 * BS_CH * D;
+      const float* s_xmi = s_xmt + D;
+      const float* s_dzmt = s_xmi + D;
+      const float* s_dzmi = s_dzmt + D;
+      const float* s_gmt = s_dzmi + D;
+      const float* s_gmi = s_gmt + D;
+      float* sc = s_sc + stage * BS_CH * 8;
+      // 1. per-candidate scalars (enable mask model.py:122, sigmoid backward of the edge update)
+      if (tid < n) {
+        const long long r = r0 + tid;
+        sc[tid * 8 + 0] = a.edges_in[r] * a.en[0];
+        sc[tid * 8 + 1] = a.edges_in[BC + r] * a.en[1];
+        sc[tid * 8 + 2] = a.edges_in[2 * BC + r] * a.en[2];
+        sc[tid * 8 + 3] = a.edges_in[3 * BC + r] * a.en[3];
+        float ds[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FULL) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float o = a.edges_out[q * BC + r];
+            ds[q] = a.dedges_out[q * BC + r] * o * (1.f - o);
+          }
+          dbeta_mt += (ds[0] + ds[1]) * invD;
+          dbeta_mi += (ds[2] + ds[3]) * invD;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sc[tid * 8 + 4 + q] = ds[q];
+      }
+      mbar_wait(full_bar(stage), phase, nullptr, 0);
+      named_bar_sync(1, BS_CONS);
+      // 2. column phase 1: sums over candidates that need the ORIGINAL dz / x rows
+      for (int c = 0; c < n; ++c) {
+        const float e0 = sc[c * 8], e1 = sc[c * 8 + 1], e2 = sc[c * 8 + 2], e3 = sc[c * 8 + 3];
+        const float dze0 = DZet[c * D + col0], dze1 = DZet[c * D + col1];
+        A_mt[0] += e0 * dze0; A_mt[1] += e0 * dze1;
+        A_mi[0] += e2 * dze0; A_mi[1] += e2 * dze1;
+        if (FULL) {
+          const float dzi0 = DZei[c * D + col0], dzi1 = DZei[c * D + col1];
+          A_mt[0] += e1 * dzi0; A_mt[1] += e1 * dzi1;
+          A_mi[0] += e3 * dzi0; A_mi[1] += e3 * dzi1;
+          const float d0 = sc[c * 8 + 4] * invD, d1 = sc[c * 8 + 5] * invD, d2 = sc[c * 8 + 6] * invD, d3 = sc[c * 8 + 7] * invD;
+          if (!ln) {                                                            // layer-0 rows are already activated;
+            const float xe0 = Xet[c * D + col0], xe1 = Xet[c * D + col1];       // with a LayerNorm in front the
+            const float xi0 = Xei[c * D + col0], xi1 = Xei[c * D + col1];       // g sums wait for column phase 2
+            G_mt[0] += d0 * xe0 + d1 * xi0; G_mt[1] += d0 * xe1 + d1 * xi1;
+            G_mi[0] += d2 * xe0 + d3 * xi0; G_mi[1] += d2 * xe1 + d3 * xi1;
+          }
+        }
+      }
+      named_bar_sync(1, BS_CONS);
+      // 3. row phase: one warp per vertex row (et rows first, then ei rows)
+      for (int q = warp; q < 2 * n; q += BS_NW) {
+        const int kind = q >= n, c = kind ? q - n : q;
+        float* xrow = (kind ? Xei : Xet) + c * D;
+        float* drow = (kind ? DZei : DZet) + c * D;
+        const bool has_dz = FULL || !kind;
+        const float e_mt = sc[c * 8 + (kind ? 1 : 0)], e_mi = sc[c * 8 + (kind ? 3 : 2)];
+        const float ds_mt = sc[c * 8 + 4 + (kind ? 1 : 0)], ds_mi = sc[c * 8 + 4 + (kind ? 3 : 2)];
+        RowT<D> x, d, xhat, dact;
+        row_load<D>(x, xrow, lane);
+        if (has_dz) {
+          row_load<D>(d, drow, lane);
+        } else {
+#pragma unroll
+          for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] = 0.f;
+        }
+        float rstd = 0.f;
+        if (ln) {
+          xhat = x;
+          rstd = row_ln_gelu_recompute<D>(xhat, x, dact, s_gamma, s_beta, lane);     // x := activated row
+        }
+        float pd_mt = row_dot<D>(x, s_dzmt, lane);
+        float pd_mi = FULL ? row_dot<D>(x, s_dzmi, lane) : 0.f;
+        float q_mt = has_dz ? row_dot<D>(d, s_xmt, lane) : 0.f;
+        float q_mi = has_dz ? row_dot<D>(d, s_xmi, lane) : 0.f;
+        pd_mt = warp_sum(pd_mt); q_mt = warp_sum(q_mt); q_mi = warp_sum(q_mi);
+        if (FULL) pd_mi = warp_sum(pd_mi);
+        if (lane == 0) {
+          float* dd = s_dots + (c * 2 + kind) * 4;
+          dd[0] = pd_mt; dd[1] = pd_mi; dd[2] = q_mt; dd[3] = q_mi;
+        }
+        const float ec_mt = e_mt * invC, ec_mi = e_mi * invC, dd_mt = ds_mt * invD, dd_mi = ds_mi * invD;
+#pragma unroll
+        for (int j = 0; j < RowT<D>::NV; ++j) {
+          const int off = (j * 32 + lane) * 4;
+          const float4 zmt = *reinterpret_cast<const float4*>(s_dzmt + off);
+          d.v[4 * j] += ec_mt * zmt.x; d.v[4 * j + 1] += ec_mt * zmt.y; d.v[4 * j + 2] += ec_mt * zmt.z; d.v[4 * j + 3] += ec_mt * zmt.w;
+          if (FULL) {
+            const float4 zmi = *reinterpret_cast<const float4*>(s_dzmi + off);
+            const float4 gmt = *reinterpret_cast<const float4*>(s_gmt + off);
+            const float4 gmi = *reinterpret_cast<const float4*>(s_gmi + off);
+            d.v[4 * j] += ec_mi * zmi.x + dd_mt * gmt.x + dd_mi * gmi.x;
+            d.v[4 * j + 1] += ec_mi * zmi.y + dd_mt * gmt.y + dd_mi * gmi.y;
+            d.v[4 * j + 2] += ec_mi * zmi.z + dd_mt * gmt.z + dd_mi * gmi.z;
+            d.v[4 * j + 3] += ec_mi * zmi.w + dd_mt * gmt.w + dd_mi * gmi.w;
+          }
+        }
+        const long long orow = (kind ? 2 * B + BC : 2 * B) + r0 + c;      // row in the [mt; mi; et; ei] layout
+        if (ln) {
+          // dy = dL/da * gelu'(y); keep xhat and dy in the ring for the parameter-gradient column phase
+          float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < RowT<D>::NV; ++j) {
+            const int off = (j * 32 + lane) * 4;
+            const float4 g = *reinterpret_cast<const float4*>(s_gamma + off);
+            const float gg[4] = {g.x, g.y, g.z, g.w};
+            float4 dy4;
+            float* dyp = reinterpret_cast<float*>(&dy4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float dy = d.v[4 * j + t] * dact.v[4 * j + t];
+              dyp[t] = dy;
+              const float dxh = dy * gg[t];
+              d.v[4 * j + t] = dxh;
+              m1 += dxh;
+              m2 += dxh * xhat.v[4 * j + t];
+            }
+            *reinterpret_cast<float4*>(drow + off) = dy4;
+            *reinterpret_cast<float4*>(xrow + off) =
+                make_float4(xhat.v[4 * j], xhat.v[4 * j + 1], xhat.v[4 * j + 2], xhat.v[4 * j + 3]);
+          }
+          m1 = warp_sum(m1) * (1.0f / D);
+          m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+          for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] = rstd * (d.v[i] - m1 - xhat.v[i] * m2);
+          if (lane == 0) {
+            float* ss = s_stat + (c * 2 + kind) * 4;
+            ss[0] = rstd; ss[1] = m1; ss[2] = m2;
+          }
+        } else {
+          row_store<D>(d, drow, lane);                    // dL/dx stays in the ring for the bias-gradient sums
+        }
+        row_store_planes<D>(d, a.dcand_hi + orow * D, a.dcand_lo ? a.dcand_lo + orow * D : nullptr, lane);
+      }
+      named_bar_sync(1, BS_CONS);
+      // 4. edge gradients (the enable mask is applied again on the way back) and column phase 2
+      if (a.dedges_in && tid < n) {
+        const float* de = s_dots + (tid * 2 + 0) * 4;     // et row
+        const float* di = s_dots + (tid * 2 + 1) * 4;     // ei row
+        const long long r = r0 + tid;
+        a.dedges_in[r] = (de[0] * invC + de[2] + sc[tid * 8 + 4]) * a.en[0];
+        a.dedges_in[BC + r] = (di[0] * invC + di[2] + sc[tid * 8 + 5]) * a.en[1];
+        a.dedges_in[2 * BC + r] = (de[1] * invC + de[3] + sc[tid * 8 + 6]) * a.en[2];
+        a.dedges_in[3 * BC + r] = (di[1] * invC + di[3] + sc[tid * 8 + 7]) * a.en[3];
+      }
+      if (ln) {
+        const float g0 = s_gamma[col0], g1 = s_gamma[col1];
+        for (int c = 0; c < n; ++c) {
+#pragma unroll
+          for (int kind = 0; kind < 2; ++kind) {
+            const float* xr = (kind ? Xei : Xet) + c * D;
+            const float* dr = (kind ? DZei : DZet) + c * D;
+            const float* ss = s_stat + (c * 2 + kind) * 4;
+            const float rstd = ss[0], m1 = ss[1], m2 = ss[2];
+            const float dy0 = dr[col0], dy1 = dr[col1], xh0 = xr[col0], xh1 = xr[col1];
+            part[0][0] += dy0 * xh0; part[0][1] += dy1 * xh1;                       // dgamma
+            part[1][0] += dy0; part[1][1] += dy1;                                   // dbeta (LayerNorm)
+            part[2][0] += rstd * (g0 * dy0 - m1 - xh0 * m2);                        // db_h = sum dL/dh
+            part[2][1] += rstd * (g1 * dy1 - m1 - xh1 * m2);
+            if (FULL) {   // middle layers (L >= 3): g sums need the activated vertex, recomputed from xhat
+              const float a0 = gelu_f(fmaf(xh0, g0, s_beta[col0])), a1 = gelu_f(fmaf(xh1, g1, s_beta[col1]));
+              const float dm = sc[c * 8 + 4 + kind] * invD, di = sc[c * 8 + 6 + kind] * invD;   // edges (mt,row), (mi,row)
+              G_mt[0] += dm * a0; G_mt[1] += dm * a1;
+              G_mi[0] += di * a0; G_mi[1] += di * a1;
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < n; ++c) {
+          part[0][0] += DZet[c * D + col0]; part[0][1] += DZet[c * D + col1];       // db_et
+          part[1][0] += DZei[c * D + col0]; part[1][1] += DZei[c * D + col1];       // db_ei
+        }
+      }
+      if (k == nchunks - 1) {
+        // 5. mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
+        a.dxm[(long long)b * D + col0] = s_dzmt[col0] + A_mt[0];
+        a.dxm[(long long)b * D + col1] = s_dzmt[col1] + A_mt[1];
+        a.dxm[(B + b) * D + col0] = (FULL ? s_dzmi[col0] : 0.f) + A_mi[0];
+        a.dxm[(B + b) * D + col1] = (FULL ? s_dzmi[col1] : 0.f) + A_mi[1];
+        if (FULL) {
+          bf16 h, l;
+          split_bf16(G_mt[0], h, l);
+          a.dg_hi[(long long)b * D + col0] = h; if (a.dg_lo) a.dg_lo[(long long)b * D + col0] = l;
+          split_bf16(G_mt[1], h, l);
+          a.dg_hi[(long long)b * D + col1] = h; if (a.dg_lo) a.dg_lo[(long long)b * D + col1] = l;
+          split_bf16(G_mi[0], h, l);
+          a.dg_hi[(B + b) * D + col0] = h; if (a.dg_lo) a.dg_lo[(B + b) * D + col0] = l;
+          split_bf16(G_mi[1], h, l);
+          a.dg_hi[(B + b) * D + col1] = h; if (a.dg_lo) a.dg_lo[(B + b) * D + col1] = l;
+          if (warp == 0) {
+            const float t0 = warp_sum(dbeta_mt), t1 = warp_sum(dbeta_mi);
+            if (lane == 0) {
+              a.dbeta[b] = t0;
+              a.dbeta[B + b] = t1;
+            }
+          }
+        }
+      }
+      // release the stage: generic-proxy accesses are ordered before the producer's next bulk copy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (++stage == BS_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  }
+  // 6. per-thread column partials -> partials[cta][v][col]  (reduced by colsum_reduce in fixed order)
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    a.partials[((long long)blockIdx.x * 3 + v) * D + col0] = part[v][0];
+    a.partials[((long long)blockIdx.x * 3 + v) * D + col1] = part[v][1];
+  }
+}
+
+static bool bwd_use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DRIN_BWD_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
+  if (!bwd_use_v1()) {
+    // persistent: every CTA of the fixed partial-sum grid must write its partials, so launch all BW_CTAS CTAs
+    const size_t smem = (size_t)(BS_STAGES * (4 * BS_CH + 6) * D + 2 * D + 2 * BS_CH * 8 + 2 * BS_CH * 8) * sizeof(float);
+    if (a.full) {
+      DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_stream_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gcn_layer_bwd_stream_kernel<D, true><<<BS_GRID, BS_THREADS, smem, stream>>>(a);
+    } else {
+      DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_stream_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gcn_layer_bwd_stream_kernel<D, false><<<BS_GRID, BS_THREADS, smem, stream>>>(a);
+    }
+    DRIN_LAUNCH_CHECK();
+    return DRIN_OK;
+  }
   if (a.full) {
     const size_t smem = (size_t)(8 + 7 * BW_NW) * D * sizeof(float) + 2 * BW_NW * sizeof(float);
     DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -481,18 +825,18 @@ int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const
 // colsum_reduce: out_v[col] = sum over sources and CTAs of partials[(cta * nvec + v) * D + col]
 // ---------------------------------------------------------------------------------------------
 // block = 32 columns x 8 CTA-slices; slice s sums partial rows s, s+8, ... then a fixed-order smem reduce
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
-                                                            int ctas, int nvec, int D, float* out0, float* out1,
-                                                            float* out2) {
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ src0, int ctas0,
+                                                            const float* __restrict__ src1, int ctas1, int nvec, int D,
+                                                            float* out0, float* out1, float* out2) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;                  // flat (v, col)
   float t = 0.f;
   if (i < nvec * D) {
     const int v = i / D, col = i - v * D;
-    for (int c = slice; c < ctas; c += 8) t += src0[((long long)c * nvec + v) * D + col];
+    for (int c = slice; c < ctas0; c += 8) t += src0[((long long)c * nvec + v) * D + col];
     if (src1)
-      for (int c = slice; c < ctas; c += 8) t += src1[((long long)c * nvec + v) * D + col];
+      for (int c = slice; c < ctas1; c += 8) t += src1[((long long)c * nvec + v) * D + col];
   }
   red[slice][lane] = t;
   __syncthreads();
@@ -506,15 +850,16 @@ __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restr
   }
 }
 
-int colsum_reduce(cudaStream_t stream, const float* src0, const float* src1, int nvec, int D, float* out0, float* out1,
-                  float* out2) {
+int colsum_reduce(cudaStream_t stream, const float* src0, int ctas0, const float* src1, int ctas1, int nvec, int D,
+                  float* out0, float* out1, float* out2) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   const int n = nvec * D;
-  colsum_reduce_kernel<<<(n + 31) / 32, 256, 0, stream>>>(src0, src1, BW_CTAS, nvec, D, out0, out1, out2);
+  colsum_reduce_kernel<<<(n + 31) / 32, 256, 0, stream>>>(src0, ctas0, src1, ctas1, nvec, D, out0, out1, out2);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }
 
 int backward_ctas() { return BW_CTAS; }
+int layer_bwd_ctas() { return bwd_use_v1() ? BW_CTAS : BS_GRID; }
 
 }  // namespace drin

@@ -111,9 +111,10 @@ struct MentionBwdArgs {
 int mention_bwd_finish(cudaStream_t stream, const MentionBwdArgs& a);
 int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const float* b_v, const float* fu,
                long long rows, bf16* out_hi, bf16* out_lo, float* partials);
-int colsum_reduce(cudaStream_t stream, const float* src0, const float* src1, int nvec, int D, float* out0, float* out1,
-                  float* out2);
-int backward_ctas();
+int colsum_reduce(cudaStream_t stream, const float* src0, int ctas0, const float* src1, int ctas1, int nvec, int D,
+                  float* out0, float* out1, float* out2);
+int backward_ctas();      // grid of score_bwd / mention_bwd_finish / dfu_finish (rows of their partial buffers)
+int layer_bwd_ctas();     // grid of gcn_layer_bwd
 
 // loss.cu
 size_t triplet_scratch_bytes(int B, int C);
