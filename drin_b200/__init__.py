@@ -6,9 +6,9 @@ Python host side that mirrors the reference's module interface.
 from .model import Model  # noqa: F401
 from .loss import TripletLoss, TopkAccuracy  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from .trainer import Trainer  # noqa: F401
+from .trainer import HostFeeder, Trainer  # noqa: F401
 
-__all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "install_as_reference_module"]
+__all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "HostFeeder", "install_as_reference_module"]
 
 
 def install_as_reference_module() -> None:

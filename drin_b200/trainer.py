@@ -13,7 +13,7 @@ Data parallelism: mentions are sharded across ranks, parameters r
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -82,3 +82,87 @@ class Trainer:
         scores, _ = m._engine.forward(inputs, m._param_views(), training=False,
                                       num_candidates_model=m.num_candidates_model)
         return gather_rows(scores, self.group) if gather else scores
+
+
+class HostFeeder:
+    """Host -> device path for the loader's CPU batches (what Lightning's ``batch.to(device)`` does before
+    reference train.py:46), double buffered on a side stream and copying only the bytes the path reads:
+
+    * ``mention_text_feature`` is ``[B, 128, 768]`` (393 KB/mention) but the model only ever reads the rows
+      ``start:end`` of each mention (ghmfc.py:55-60): the span rows are gathered on the host into a pinned
+      ``[B, Ls, 768]`` buffer (``Ls`` = longest span of the batch) and start/end are rebased to ``0:len``;
+    * ``mention_text_mask`` is never read by the DRIN configuration (ghmfc.py:25-26): a tiny placeholder is sent.
+
+    Everything else is copied as is.  ``last_bytes`` is the number of bytes actually moved for the last batch.
+    """
+
+    def __init__(self, device, slots: int = 2, compact_spans: bool = True):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict() for _ in range(slots)]
+        self.next_slot = 0
+        self.compact_spans = compact_spans
+        self.last_bytes = 0
+
+    def _pinned(self, slot, name, shape, dtype):
+        t = slot.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype).pin_memory()
+            slot[name] = t
+        return t
+
+    def _dev(self, slot, name, like):
+        t = slot.get(name)
+        if t is None or tuple(t.shape) != tuple(like.shape) or t.dtype != like.dtype:
+            t = torch.empty(like.shape, dtype=like.dtype, device=self.device)
+            slot[name] = t
+        return t
+
+    def submit(self, host_batch: Sequence[torch.Tensor]) -> int:
+        """Start moving one CPU batch (14 inputs [+ labels]); returns the slot to pass to ``get``."""
+        sid = self.next_slot
+        self.next_slot = (self.next_slot + 1) % len(self.slots)
+        slot = self.slots[sid]
+        srcs = list(host_batch)
+        mtf, start, end = srcs[0], srcs[2], srcs[3]
+        Lm = mtf.shape[1]
+        ok = self.compact_spans and bool(((start >= 0) & (end >= start) & (end <= Lm)).all())
+        if ok:
+            lens = end - start
+            Ls = max(int(lens.max()), 1)
+            idx = (start.unsqueeze(1) + torch.arange(Ls)).clamp_(max=Lm - 1)               # [B, Ls]
+            compact = self._pinned(slot, "h_mtf", (mtf.shape[0], Ls, mtf.shape[2]), mtf.dtype)
+            torch.gather(mtf, 1, idx.unsqueeze(-1).expand(-1, -1, mtf.shape[2]), out=compact)
+            h_start = self._pinned(slot, "h_start", start.shape, start.dtype).zero_()
+            h_end = self._pinned(slot, "h_end", end.shape, end.dtype).copy_(lens)
+            h_mask = self._pinned(slot, "h_mask", (mtf.shape[0], 1), torch.int64).zero_()
+            srcs[0], srcs[1], srcs[2], srcs[3] = compact, h_mask, h_start, h_end
+        else:
+            srcs = [t if t.is_pinned() else t.pin_memory() for t in srcs]
+        done = slot.get("used")
+        with torch.cuda.stream(self.stream):
+            if done is not None:
+                self.stream.wait_event(done)           # the previous consumer of this slot has finished
+            out, nbytes = [], 0
+            for i, h in enumerate(srcs):
+                d = self._dev(slot, f"d{i}", h)
+                d.copy_(h, non_blocking=True)
+                nbytes += h.numel() * h.element_size()
+                out.append(d)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        slot["batch"], slot["ready"] = out, ev
+        self.last_bytes = nbytes
+        return sid
+
+    def get(self, sid: int) -> List[torch.Tensor]:
+        """Device batch of a submitted slot; the current stream waits for its copy."""
+        slot = self.slots[sid]
+        torch.cuda.current_stream(self.device).wait_event(slot["ready"])
+        return slot["batch"]
+
+    def release(self, sid: int) -> None:
+        """Call after the work that reads the slot has been enqueued on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.slots[sid]["used"] = ev

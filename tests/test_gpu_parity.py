@@ -132,3 +132,20 @@ def test_rejects_bad_batches():
         model(bad)
     with pytest.raises(ValueError):
         model([t.cuda() for t in batch[:5]])
+
+
+def test_host_feeder_compact_spans_is_bit_identical():
+    """The host path that ships only the start:end rows of mention_text_feature gives the same bits as the
+    verbatim copy (the other rows are never read by the reference, ghmfc.py:55-60)."""
+    cfg, batch, sd, _ = load_case(CASES[2])
+    model = _cuda_model(cfg, sd)
+    tr = drin_b200.Trainer(model, margin=cfg.triplet_margin)
+    outs = []
+    for compact in (False, True):
+        feeder = drin_b200.HostFeeder("cuda", compact_spans=compact)
+        sid = feeder.submit(batch)
+        outs.append(tr.rank_scores(feeder.get(sid)).clone())
+        feeder.release(sid)
+        if compact:
+            assert feeder.last_bytes < sum(t.numel() * t.element_size() for t in batch) // 1.5
+    assert torch.equal(outs[0], outs[1])
