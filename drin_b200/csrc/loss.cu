@@ -6,90 +6,151 @@
 //     p_i  = sum_c s[i,c] * y[i,c]   (0 when the gold entity is not among the candidates)
 //     dL/ds[b,c] = k * ( A[b,c] - y[b,c] * N_b ),
 //        A[b,c] = #{ i : s[b,c] - p_i + margin > 0 },  N_b = #{ (b',c') : s[b',c'] - p_b + margin > 0 }.
-// Under data parallelism every rank holds the gathered global score matrix and evaluates its own rows:
-// counts are integers (order-independent atomics) and the hinge sum is reduced in a fixed order in
-// double precision, so the result is bit-reproducible.
+// Under data parallelism every rank holds the gathered global score matrix and evaluates its own rows.
+// Counts come from binary searches in sorted arrays (CUB radix sort of the positives and of the scores) and the
+// hinge sum is reduced in a fixed order in double precision, so the result is bit-reproducible.
+#include <cub/cub.cuh>
+
 #include "kernels.cuh"
 
 namespace drin {
 
 static constexpr int TL_THREADS = 256;
-static constexpr int TL_TILE = 2048;
 
+// O(N log N) evaluation: with the positives p sorted ascending (prefix sums P) and all global scores sorted,
+//   A[b,c]      = lower_bound(p_sorted, s + m)                       (# p_i < s + m)
+//   hinge[b,c]  = A * (s + m) - P[A]                                 (sum_i max(s - p_i + m, 0), in double)
+//   N_b         = n_scores - upper_bound(s_sorted, p_b - m)          (# s' > p_b - m)
+// so a rank pays O((B_loc C + B_glob C) log) instead of O(B_loc B_glob C) -- this is what keeps the loss flat when
+// the global batch grows with the number of GPUs.
 struct TripletScratch {
-  float* p;          // [B]
-  int* n;            // [B]
-  double* partial;   // [blocks]
+  float* p;            // [B]
+  float* p_sorted;     // [B]
+  double* prefix;      // [B + 1]
+  float* s;            // [B * (C-1)] compacted global scores
+  float* s_sorted;     // [B * (C-1)]
+  int* n;              // [B]
+  double* partial;     // [blocks]
+  void* cub_temp;
+  size_t cub_bytes;
 };
 
-static TripletScratch carve_triplet(void* scratch, int B, size_t* bytes) {
+static size_t cub_sort_bytes(size_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const float*)nullptr, (float*)nullptr, (int)n);
+  return bytes;
+}
+
+static TripletScratch carve_triplet(void* scratch, int B, int C, size_t* bytes) {
   TripletScratch t;
   size_t off = 0;
   char* base = static_cast<char*>(scratch);
-  t.p = reinterpret_cast<float*>(base + off);
-  off = align_up(off + sizeof(float) * B, 256);
-  t.n = reinterpret_cast<int*>(base + off);
-  off = align_up(off + sizeof(int) * B, 256);
-  t.partial = reinterpret_cast<double*>(base + off);
-  off = align_up(off + sizeof(double) * 65536, 256);
+  const size_t ns = (size_t)B * (C - 1);
+  auto take = [&](size_t nbytes) {
+    char* ptr = base ? base + off : nullptr;
+    off = align_up(off + nbytes, 256);
+    return ptr;
+  };
+  t.p = reinterpret_cast<float*>(take(sizeof(float) * B));
+  t.p_sorted = reinterpret_cast<float*>(take(sizeof(float) * B));
+  t.prefix = reinterpret_cast<double*>(take(sizeof(double) * (B + 1)));
+  t.s = reinterpret_cast<float*>(take(sizeof(float) * ns));
+  t.s_sorted = reinterpret_cast<float*>(take(sizeof(float) * ns));
+  t.n = reinterpret_cast<int*>(take(sizeof(int) * B));
+  t.partial = reinterpret_cast<double*>(take(sizeof(double) * 65536));
+  t.cub_bytes = 2 * ns * sizeof(float) + (4u << 20);      // upper bound of the radix-sort temp storage (checked at run time)
+  t.cub_temp = take(t.cub_bytes);
   if (bytes) *bytes = off;
   return t;
 }
 
 size_t triplet_scratch_bytes(int B, int C) {
-  (void)C;
   size_t bytes = 0;
-  carve_triplet(nullptr, B, &bytes);
+  carve_triplet(nullptr, B, C, &bytes);
   return bytes;
 }
 
+// p[i] = sum_c s[i,c] y[i,c]; compact the real-candidate scores (drops the gold slot, utils.py:36-37)
 __global__ void triplet_pos_kernel(const float* __restrict__ s, const unsigned char* __restrict__ y, int B, int C,
-                                   float* __restrict__ p, int* __restrict__ n) {
+                                   float* __restrict__ p, float* __restrict__ sc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float acc = 0.f;
-  for (int c = 0; c < C - 1; ++c) acc += s[(long long)i * C + c] * (float)y[(long long)i * (C - 1) + c];
+  for (int c = 0; c < C - 1; ++c) {
+    const float v = s[(long long)i * C + c];
+    acc += v * (float)y[(long long)i * (C - 1) + c];
+    sc[(long long)i * (C - 1) + c] = v;
+  }
   p[i] = acc;
-  n[i] = 0;
 }
 
-// one thread per local score element; loops over all positives
+// single-block exclusive prefix sums in double: prefix[j] = sum_{i<j} p_sorted[i], j = 0..B
+__global__ void __launch_bounds__(1024) triplet_prefix_kernel(const float* __restrict__ ps, int B, double* __restrict__ prefix) {
+  __shared__ double tot[1024];
+  const int t = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  const int i0 = t * per, i1 = min(B, i0 + per);
+  double acc = 0.0;
+  for (int i = i0; i < i1; ++i) acc += (double)ps[i];
+  tot[t] = acc;
+  __syncthreads();
+  if (t == 0) {
+    double run = 0.0;
+    for (int i = 0; i < 1024; ++i) {
+      const double v = tot[i];
+      tot[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  double run = tot[t];
+  for (int i = i0; i < i1; ++i) {
+    prefix[i] = run;
+    run += (double)ps[i];
+  }
+  if (i0 < B && i1 == B) prefix[B] = run;
+}
+
+__device__ __forceinline__ int lower_bound_f(const float* __restrict__ a, int n, float v) {   // # a[i] < v
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound_f(const float* __restrict__ a, int n, float v) {   // # a[i] <= v
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// one thread per local score element
 __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* __restrict__ s,
-                                                                   const float* __restrict__ p, int B, int C, int row0,
-                                                                   int rows, float margin, float k,
+                                                                   const float* __restrict__ ps,
+                                                                   const double* __restrict__ prefix, int B, int C,
+                                                                   int row0, int rows, float margin, float k,
                                                                    float* __restrict__ dscores,
                                                                    double* __restrict__ partial) {
-  __shared__ float sp[TL_TILE];
   __shared__ double sred[TL_THREADS / 32];
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // over rows * (C-1)
   const long long total = (long long)rows * (C - 1);
-  const bool live = e < total;
-  const int bl = live ? (int)(e / (C - 1)) : 0;
-  const int c = live ? (int)(e - (long long)bl * (C - 1)) : 0;
-  const float sm = live ? s[(long long)(row0 + bl) * C + c] + margin : 0.f;
-  int cnt = 0;
-  float hinge = 0.f;
-  double hinge_d = 0.0;
-  for (int t0 = 0; t0 < B; t0 += TL_TILE) {
-    const int nt = min(TL_TILE, B - t0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) sp[i] = p[t0 + i];
-    __syncthreads();
-    if (live) {
-      for (int i = 0; i < nt; ++i) {
-        const float d = sm - sp[i];
-        cnt += d > 0.f;
-        hinge += fmaxf(d, 0.f);
-      }
-      hinge_d += (double)hinge;     // flush the fp32 tile sum into double every tile
-      hinge = 0.f;
-    }
+  double hinge = 0.0;
+  if (e < total) {
+    const int bl = (int)(e / (C - 1));
+    const int c = (int)(e - (long long)bl * (C - 1));
+    const float sm = s[(long long)(row0 + bl) * C + c] + margin;
+    const int A = lower_bound_f(ps, B, sm);            // s - p_i + margin > 0  <=>  p_i < s + margin
+    hinge = (double)A * (double)sm - prefix[A];
+    if (sm != sm) hinge = (double)sm;                  // NaN scores poison the loss like upstream
+    dscores[(long long)bl * C + c] = k * (float)A;
   }
-  if (live) dscores[(long long)bl * C + c] = k * (float)cnt;
-  // fixed-order block reduction of the hinge sum
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) hinge_d += __shfl_xor_sync(0xffffffffu, hinge_d, o);
-  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = hinge_d;
+  for (int o = 16; o > 0; o >>= 1) hinge += __shfl_xor_sync(0xffffffffu, hinge, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = hinge;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
@@ -98,26 +159,12 @@ __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* 
   }
 }
 
-// N_b for local b: blockIdx.y = tile of local rows (one thread per row), blockIdx.x = chunk of global scores
-__global__ void __launch_bounds__(TL_THREADS) triplet_n_kernel(const float* __restrict__ s, const float* __restrict__ p,
-                                                               int B, int C, int row0, int rows, float margin,
-                                                               int* __restrict__ n) {
-  __shared__ float ss[TL_TILE];
-  const long long total = (long long)B * (C - 1);
-  const long long e0 = (long long)blockIdx.x * TL_TILE;
-  const int ne = (int)min((long long)TL_TILE, total - e0);
-  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
-    const long long e = e0 + i;
-    const long long b = e / (C - 1);
-    ss[i] = s[b * C + (e - b * (C - 1))];
-  }
-  __syncthreads();
-  const int bl = blockIdx.y * blockDim.x + threadIdx.x;
+// N_b for the local rows: # global scores with s' > p_b - margin
+__global__ void triplet_n_kernel(const float* __restrict__ ss, long long ns, const float* __restrict__ p, int row0,
+                                 int rows, float margin, int* __restrict__ n) {
+  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= rows) return;
-  const float thr = p[row0 + bl] - margin;
-  int cnt = 0;
-  for (int i = 0; i < ne; ++i) cnt += ss[i] > thr;      // s - p + margin > 0
-  if (cnt) atomicAdd(n + row0 + bl, cnt);
+  n[row0 + bl] = (int)(ns - upper_bound_f(ss, (int)ns, p[row0 + bl] - margin));
 }
 
 __global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const int* __restrict__ n, int C, int row0,
@@ -145,18 +192,32 @@ int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* 
   if (B <= 0 || C <= 1 || row0 < 0 || rows <= 0 || row0 + rows > B)
     return fail(DRIN_ERR_ARG, "triplet_loss: bad shape B=%d C=%d row0=%d rows=%d", B, C, row0, rows);
   if (!scores || !labels || !loss || !dscores || !scratch) return fail(DRIN_ERR_ARG, "triplet_loss: null argument");
-  TripletScratch t = carve_triplet(scratch, B, nullptr);
+  if ((long long)B * (C - 1) > 0x7fffffffLL) return fail(DRIN_ERR_ARG, "triplet_loss: batch too large");
+  TripletScratch t = carve_triplet(scratch, B, C, nullptr);
+  const long long ns = (long long)B * (C - 1);
   const float k = (float)(1.0 / ((double)B * (double)B * (double)(C - 1)));
-  triplet_pos_kernel<<<(B + 255) / 256, 256, 0, stream>>>(scores, labels, B, C, t.p, t.n);
+  triplet_pos_kernel<<<(B + 255) / 256, 256, 0, stream>>>(scores, labels, B, C, t.p, t.s);
+  DRIN_LAUNCH_CHECK();
+  size_t need = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, need, t.p, t.p_sorted, B);
+  if (need > t.cub_bytes) return fail(DRIN_ERR_WORKSPACE, "triplet_loss: sort temp %zu > %zu", need, t.cub_bytes);
+  size_t tmp = t.cub_bytes;
+  DRIN_CUDA(cub::DeviceRadixSort::SortKeys(t.cub_temp, tmp, t.p, t.p_sorted, B, 0, 32, stream));
+  count_launch();
+  cub::DeviceRadixSort::SortKeys(nullptr, need, t.s, t.s_sorted, (int)ns);
+  if (need > t.cub_bytes) return fail(DRIN_ERR_WORKSPACE, "triplet_loss: sort temp %zu > %zu", need, t.cub_bytes);
+  tmp = t.cub_bytes;
+  DRIN_CUDA(cub::DeviceRadixSort::SortKeys(t.cub_temp, tmp, t.s, t.s_sorted, (int)ns, 0, 32, stream));
+  count_launch();
+  triplet_prefix_kernel<<<1, 1024, 0, stream>>>(t.p_sorted, B, t.prefix);
   DRIN_LAUNCH_CHECK();
   const long long local = (long long)rows * (C - 1);
   const int cblocks = (int)((local + TL_THREADS - 1) / TL_THREADS);
   if (cblocks > 65536) return fail(DRIN_ERR_ARG, "triplet_loss: too many local scores (%lld)", local);
-  triplet_count_kernel<<<cblocks, TL_THREADS, 0, stream>>>(scores, t.p, B, C, row0, rows, margin, k, dscores, t.partial);
+  triplet_count_kernel<<<cblocks, TL_THREADS, 0, stream>>>(scores, t.p_sorted, t.prefix, B, C, row0, rows, margin, k,
+                                                           dscores, t.partial);
   DRIN_LAUNCH_CHECK();
-  const long long total = (long long)B * (C - 1);
-  dim3 ngrid((unsigned)((total + TL_TILE - 1) / TL_TILE), (unsigned)((rows + TL_THREADS - 1) / TL_THREADS));
-  triplet_n_kernel<<<ngrid, TL_THREADS, 0, stream>>>(scores, t.p, B, C, row0, rows, margin, t.n);
+  triplet_n_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(t.s_sorted, ns, t.p, row0, rows, margin, t.n);
   DRIN_LAUNCH_CHECK();
   const long long fe = (long long)rows * C;
   triplet_finish_kernel<<<(int)((fe + 255) / 256), 256, 0, stream>>>(labels, t.n, C, row0, rows, k, dscores, t.partial,
