@@ -15,6 +15,8 @@
 // (tcgen05.ld -> bias -> global / split planes).  Two 256-column TMEM accumulators let the epilogue
 // of tile i overlap the MMAs of tile i+1.  All mbarrier waits carry a watchdog so a protocol bug traps
 // instead of hanging the GPU.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -29,10 +31,10 @@ static constexpr int BN = 256;
 static constexpr int BK = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;
 static constexpr int A_PLANE_BYTES = BM * BK * 2;   // 16 KB
-static constexpr int B_PLANE_BYTES = BN * BK * 2;   // 32 KB
+static constexpr int B_PLANE_BYTES = BN * BK * 2;   // 32 KB (16 KB per CTA in cta_group::2 mode)
 static constexpr int ACC_STAGES = 2;
 static constexpr int TMEM_COLS = ACC_STAGES * BN;   // 512
-static constexpr int MAX_STAGES = 4;
+static constexpr int MAX_STAGES = 6;
 static constexpr int GEMM_THREADS = 192;
 static constexpr int SMEM_TILE_BYTES = 192 * 1024;
 static constexpr int EPI_LD = 36;                                    // padded row (floats) of the epilogue transpose
@@ -88,6 +90,48 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// cta_group::2 forms: one MMA spans the CTA pair (M = 256: 128 rows of A and half of B from each CTA's smem,
+// 128 accumulator rows in each CTA's TMEM); issued by the leader CTA only.
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+// TMA load issued by either CTA of the pair; transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 rem;\n\t"
+      "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -112,7 +156,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -120,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B alignment
   const uint32_t bar_base = smem_base + SMEM_TILE_BYTES;
-  // barrier block: full[4] empty[4] tmem_full[2] tmem_empty[2] (8 B each) + tmem base (4 B)
+  // barrier block: full[6] empty[6] tmem_full[2] tmem_empty[2] (8 B each) + tmem base (4 B)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
@@ -130,10 +174,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  constexpr int BN_CTA = BN / CTAS;                      // B rows this CTA stages (the pair's MMA spans all BN)
+  constexpr int B_PLANE = BN_CTA * BK * 2;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = p.planes * (A_PLANE_BYTES + B_PLANE_BYTES);
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int stage_bytes = p.planes * (A_PLANE_BYTES + B_PLANE);
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;      // m_tiles counts (CTAS * 128)-row tiles
+  const int worker = blockIdx.x / CTAS, nworkers = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -148,19 +197,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);     // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 4 * CTAS);     // one arrive per epilogue warp of every CTA of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();          // peer barriers are initialised before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -177,40 +234,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   };
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
+    // ================================ TMA producer (every CTA loads its own half) ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = worker; t < total_tiles; t += nworkers) {
         int m_blk, n_blk, ks, kb0, kb1;
         tile_coords(t, m_blk, n_blk, ks);
         kblock_range(ks, kb0, kb1);
-        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int m0 = (m_blk * CTAS + (int)cta_rank) * BM;
+        const int n0 = n_blk * BN + (int)cta_rank * BN_CTA;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
           const uint32_t fb = full_bar(stage);
-          mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
+          if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(CTAS * stage_bytes));
           const uint32_t sA = smem_base + stage * stage_bytes;
           const uint32_t sB = sA + p.planes * A_PLANE_BYTES;
           const int k0 = kb * BK;
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+            if (CTAS == 1) tma_load_2d(dst, map, fb, c0, c1);
+            else tma_load_2d_2cta(dst, map, fb, c0, c1);
+          };
           for (int pl = 0; pl < p.planes; ++pl) {
             const CUtensorMap* ma = pl ? &tmA1 : &tmA0;
             const CUtensorMap* mb = pl ? &tmB1 : &tmB0;
             const uint32_t a_dst = sA + pl * A_PLANE_BYTES;
-            const uint32_t b_dst = sB + pl * B_PLANE_BYTES;
+            const uint32_t b_dst = sB + pl * B_PLANE;
             if (!A_MN) {
-              tma_load_2d(a_dst, ma, fb, k0, m0);                       // box {64 k, 128 rows}
+              load(a_dst, ma, k0, m0);                                   // box {64 k, 128 rows}
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j)                         // box {64 m, 64 k-rows}
-                tma_load_2d(a_dst + j * (BK * 128), ma, fb, m0 + 64 * j, k0);
+              for (int j = 0; j < BM / 64; ++j)                          // box {64 m, 64 k-rows}
+                load(a_dst + j * (BK * 128), ma, m0 + 64 * j, k0);
             }
             if (!B_MN) {
-              tma_load_2d(b_dst, mb, fb, k0, n0);                       // box {64 k, 256 rows}
+              load(b_dst, mb, k0, n0);                                   // box {64 k, BN_CTA rows}
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(b_dst + j * (BK * 128), mb, fb, n0 + 64 * j, k0);
+              for (int j = 0; j < BN_CTA / 64; ++j)
+                load(b_dst + j * (BK * 128), mb, n0 + 64 * j, k0);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -218,18 +280,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    // ================================ MMA issuer (leader CTA, one thread) ==================================
+    if (lane == 0 && leader) {
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accum, bf16 x bf16
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((BM * CTAS) >> 4) << 24);
       const uint32_t a_lbo = A_MN ? p.mn_lbo : 16u, a_sbo = A_MN ? p.mn_sbo : 1024u;
       const uint32_t b_lbo = B_MN ? p.mn_lbo : 16u, b_sbo = B_MN ? p.mn_sbo : 1024u;
       const uint32_t a_kstep = A_MN ? UMMA_K * 128u : UMMA_K * 2u;      // bytes per UMMA_K step
       const uint32_t b_kstep = B_MN ? UMMA_K * 128u : UMMA_K * 2u;
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (CTAS == 1) umma_bf16(d, ad, bd, idesc, acc);
+        else umma_bf16_2cta(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {
+        if (CTAS == 1) umma_commit(bar);
+        else umma_commit_2cta(bar);
+      };
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = worker; t < total_tiles; t += nworkers) {
         int m_blk, n_blk, ks, kb0, kb1;
         tile_coords(t, m_blk, n_blk, ks);
         kblock_range(ks, kb0, kb1);
@@ -246,36 +317,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t a0 = make_smem_desc(sA + k * a_kstep, a_lbo, a_sbo);
             const uint64_t b0 = make_smem_desc(sB + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16(d_tmem, a0, b0, idesc, accumulate);
+            mma(d_tmem, a0, b0, accumulate);
             accumulate = 1;
             if (p.planes == 2) {
               const uint64_t a1 = make_smem_desc(sA + A_PLANE_BYTES + k * a_kstep, a_lbo, a_sbo);
-              const uint64_t b1 = make_smem_desc(sB + B_PLANE_BYTES + k * b_kstep, b_lbo, b_sbo);
-              umma_bf16(d_tmem, a0, b1, idesc, 1u);     // hi * lo
-              umma_bf16(d_tmem, a1, b0, idesc, 1u);     // lo * hi
+              const uint64_t b1 = make_smem_desc(sB + B_PLANE + k * b_kstep, b_lbo, b_sbo);
+              mma(d_tmem, a0, b1, 1u);     // hi * lo
+              mma(d_tmem, a1, b0, 1u);     // lo * hi
             }
           }
-          umma_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+          commit(empty_bar(stage));                 // frees the smem slot (in both CTAs) when these MMAs retire
+          if (kb == kb1 - 1) commit(tfull_bar(acc));
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (kb1 <= kb0) umma_commit(tfull_bar(acc));     // empty slice (cannot happen; keeps protocol live)
+        if (kb1 <= kb0) commit(tfull_bar(acc));     // empty slice (cannot happen; keeps protocol live)
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ================================ epilogue (4 warps) ==========================
+    // ================================ epilogue (4 warps, own 128 accumulator rows) ==========================
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = worker; t < total_tiles; t += nworkers) {
       int m_blk, n_blk, ks;
       tile_coords(t, m_blk, n_blk, ks);
       mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, 4);
       tcgen05_fence_after();
       // Each thread owns one accumulator row in TMEM (32x32b shape); a padded smem transpose turns
       // that into row-contiguous 128-B global stores (4 rows x 128 B per warp instruction).
-      const long long row_base = (long long)m_blk * BM + q * 32;
+      const long long row_base = ((long long)m_blk * CTAS + cta_rank) * BM + q * 32;
       float* stg = reinterpret_cast<float*>(smem_raw + (stage_smem - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
       const int sub = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
@@ -336,17 +407,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CTAS == 1) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(tempty_bar(acc), 0u);      // the leader's MMA thread waits for both CTAs
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();          // the peer may still be read / written by the leader's MMAs
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if (CTAS == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -444,6 +523,25 @@ void gemm_debug_set_mn_desc(int lbo_bytes, int sbo_bytes) {
 
 static int g_num_sms = 0;
 static int* g_error_flag = nullptr;
+static bool g_force_1cta = false;
+
+template <bool A_MN, bool B_MN, int CTAS>
+static cudaError_t launch_gemm(int grid, cudaStream_t stream, const CUtensorMap& tA0, const CUtensorMap& tA1,
+                               const CUtensorMap& tB0, const CUtensorMap& tB1, const GemmKernelParams& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_TOTAL_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<A_MN, B_MN, CTAS>, tA0, tA1, tB0, tB1, p);
+}
 
 static int gemm_init_once() {
   static int status = -1;
@@ -451,12 +549,20 @@ static int gemm_init_once() {
   int dev = 0;
   DRIN_CUDA(cudaGetDevice(&dev));
   DRIN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_TOTAL_BYTES));
-  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_TOTAL_BYTES));
-  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_TOTAL_BYTES));
+#define DRIN_GEMM_ATTR(A, B, C)                                                                               \
+  DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 SMEM_TOTAL_BYTES))
+  DRIN_GEMM_ATTR(false, false, 1);
+  DRIN_GEMM_ATTR(false, true, 1);
+  DRIN_GEMM_ATTR(true, true, 1);
+  DRIN_GEMM_ATTR(false, false, 2);
+  DRIN_GEMM_ATTR(false, true, 2);
+  DRIN_GEMM_ATTR(true, true, 2);
+#undef DRIN_GEMM_ATTR
+  {
+    const char* e = getenv("DRIN_GEMM_1CTA");
+    g_force_1cta = e && e[0] == '1';
+  }
   DRIN_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
   DRIN_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   status = DRIN_OK;
@@ -483,8 +589,10 @@ int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const
     return fail(DRIN_ERR_ARG, "gemm: operand shapes do not match layout %d (A %lldx%d, B %lldx%d, M=%lld N=%d K=%lld)",
                 (int)layout, A.rows, A.cols, B.rows, B.cols, M, N, K);
 
+  // cta_group::2 (256 x 256 tile per CTA pair, each CTA stages half of B) whenever there are >= 2 row tiles
+  const int ctas = (!g_force_1cta && M > BM) ? 2 : 1;
   CUtensorMap tA0, tA1, tB0, tB1;
-  const int a_box = a_mn ? BK : BM, b_box = b_mn ? BK : BN;
+  const int a_box = a_mn ? BK : BM, b_box = b_mn ? BK : BN / ctas;
   DRIN_TRY(make_tmap(A.hi, A.rows, A.cols, A.ld, a_box, &tA0));
   DRIN_TRY(make_tmap(B.hi, B.rows, B.cols, B.ld, b_box, &tB0));
   if (planes == 2) {
@@ -499,14 +607,14 @@ int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const
   p.M = M;
   p.N = N;
   p.planes = planes;
-  p.stages = planes == 2 ? 2 : 4;
+  p.stages = ctas == 2 ? (planes == 2 ? 3 : 6) : (planes == 2 ? 2 : 4);      // 192 KB ring either way
   p.kblocks_total = (int)((K + BK - 1) / BK);
   if (ksplit < 1) ksplit = 1;
   if (ksplit > p.kblocks_total) ksplit = p.kblocks_total;
   p.kblocks_per_split = (p.kblocks_total + ksplit - 1) / ksplit;
   ksplit = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;   // no empty slices
   p.ksplit = ksplit;
-  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.m_tiles = (int)((M + (long long)BM * ctas - 1) / ((long long)BM * ctas));   // tiles of the CTA pair
   p.n_tiles = (N + BN - 1) / BN;
   p.bias = ksplit > 1 ? nullptr : ep.bias;
   p.ldc = ep.ldc;
@@ -526,13 +634,19 @@ int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const
     p.c_split_stride = 0;
   }
   const long long tiles = (long long)p.m_tiles * p.n_tiles * ksplit;
-  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  if (layout == GEMM_NT)
-    gemm_tcgen05_kernel<false, false><<<grid, GEMM_THREADS, SMEM_TOTAL_BYTES, stream>>>(tA0, tA1, tB0, tB1, p);
-  else if (layout == GEMM_NN)
-    gemm_tcgen05_kernel<false, true><<<grid, GEMM_THREADS, SMEM_TOTAL_BYTES, stream>>>(tA0, tA1, tB0, tB1, p);
-  else
-    gemm_tcgen05_kernel<true, true><<<grid, GEMM_THREADS, SMEM_TOTAL_BYTES, stream>>>(tA0, tA1, tB0, tB1, p);
+  const int workers = g_num_sms / ctas;
+  const int grid = ctas * (int)(tiles < workers ? tiles : workers);
+  cudaError_t le;
+  if (ctas == 1) {
+    le = layout == GEMM_NT   ? launch_gemm<false, false, 1>(grid, stream, tA0, tA1, tB0, tB1, p)
+         : layout == GEMM_NN ? launch_gemm<false, true, 1>(grid, stream, tA0, tA1, tB0, tB1, p)
+                             : launch_gemm<true, true, 1>(grid, stream, tA0, tA1, tB0, tB1, p);
+  } else {
+    le = layout == GEMM_NT   ? launch_gemm<false, false, 2>(grid, stream, tA0, tA1, tB0, tB1, p)
+         : layout == GEMM_NN ? launch_gemm<false, true, 2>(grid, stream, tA0, tA1, tB0, tB1, p)
+                             : launch_gemm<true, true, 2>(grid, stream, tA0, tA1, tB0, tB1, p);
+  }
+  DRIN_CUDA(le);
   DRIN_LAUNCH_CHECK();
   if (ksplit > 1) {
     const long long total4 = M * (long long)(N / 4);
