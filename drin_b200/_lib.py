@@ -22,7 +22,7 @@ class DrinConfig(C.Structure):
         ("batch", c_int32), ("candidates", c_int32), ("mention_tokens", c_int32), ("entity_tokens", c_int32),
         ("regions", c_int32), ("mention_objects", c_int32), ("entity_objects", c_int32), ("embed_dim", c_int32),
         ("resnet_dim", c_int32), ("gcn_layers", c_int32), ("precision", c_int32), ("training", c_int32),
-        ("edge_enabled", c_float * 4),
+        ("edge_enabled", c_float * 4), ("static_edges", c_int32),
     ]
 
 

@@ -65,9 +65,10 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
   for (int l = 0; l < L; ++l) {
     LayerWs& lw = ws.layer[l];
     lw.full = l < L - 1;
+    lw.dyn = lw.full && !c.static_edges;
     lw.rows = lw.full ? (long long)(2 * B + 2 * BC) : (long long)(B + BC);
     lw.w_h = m.planes(D * D, split);
-    if (lw.full) {
+    if (lw.dyn) {
       lw.w_u = m.planes(D * D, split);
       lw.w_v = m.planes(D * D, split);
     }
@@ -76,9 +77,9 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
       lw.xm_p = ws.xm0_p;
     } else {
       lw.xm = m.take<float>(2 * B * D);
-      if (lw.full) lw.xm_p = m.planes(2 * B * D, split);
+      if (lw.dyn) lw.xm_p = m.planes(2 * B * D, split);
     }
-    if (lw.full) {
+    if (lw.dyn) {
       lw.fu = m.take<float>(2 * B * D);
       lw.fu_p = m.planes(2 * B * D, split);
       lw.g = m.take<float>(2 * B * D);
@@ -144,7 +145,7 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
   DRIN_TRY(split_weight(stream, p.w_ei, ws.w_ei, (size_t)D * R));
   for (int l = 0; l < L; ++l) {
     DRIN_TRY(split_weight(stream, p.layer[l].w_h, ws.layer[l].w_h, (size_t)D * D));
-    if (ws.layer[l].full) {
+    if (ws.layer[l].dyn) {
       DRIN_TRY(split_weight(stream, p.layer[l].w_u, ws.layer[l].w_u, (size_t)D * D));
       DRIN_TRY(split_weight(stream, p.layer[l].w_v, ws.layer[l].w_v, (size_t)D * D));
     }
@@ -197,16 +198,22 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
     } else {
       const LayerWs& pw = ws.layer[l - 1];
       const drin_layer_params& pp = p.layer[l - 1];
-      DRIN_TRY(mention_ln(stream, D, pw.h, 2 * B, pp.ln_w, pp.ln_b, lw.xm, lw.full ? lw.xm_p.hi : nullptr,
-                          lw.full ? lw.xm_p.lo : nullptr));
+      DRIN_TRY(mention_ln(stream, D, pw.h, 2 * B, pp.ln_w, pp.ln_b, lw.xm, lw.dyn ? lw.xm_p.hi : nullptr,
+                          lw.dyn ? lw.xm_p.lo : nullptr));
       la.x_et = pw.h + 2 * B * D;
       la.x_ei = pw.h + (2 * B + BC) * D;
       la.ln_gamma = pp.ln_w;
       la.ln_beta = pp.ln_b;
-      la.edges_in = pw.edges_out;
+      if (pw.dyn) {
+        la.edges_in = pw.edges_out;
+      } else {
+        // static edges (model.py:135-136): layer l sees the input edges masked l + 1 times (model.py:122)
+        la.edges_in = ws.edges0;
+        for (int k = 0; k < 4; ++k) la.en[k] = powf(c.edge_enabled[k], (float)(l + 1));
+      }
     }
     la.xm = lw.xm;
-    if (lw.full) {
+    if (lw.dyn) {
       GemmEpilogue ep;
       ep.ldc = D; ep.ld_planes = D;
       ep.C = lw.fu; ep.bias = lp.b_u; ep.out_hi = lw.fu_p.hi; ep.out_lo = lw.fu_p.lo;

@@ -11,7 +11,8 @@ struct Planes {
 };
 
 struct LayerWs {
-  bool full = false;
+  bool full = false;           // all four vertex types are updated (every layer but the last)
+  bool dyn = false;            // dynamic edge update runs in this layer (full && !static_edges)
   long long rows = 0;          // rows of z / h: full 2B+2BC (mt, mi, et, ei), last B+BC (mt, et)
   Planes w_h, w_u, w_v;        // weight planes (w_u / w_v only for full layers)
   float* xm = nullptr;         // [2B, D] activated mention vertices entering this layer (layer 0: alias of x0)

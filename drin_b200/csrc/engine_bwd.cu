@@ -80,12 +80,18 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       la.x_ei = pw.h + (2 * B + BC) * D;
       la.ln_gamma = p.layer[l - 1].ln_w;
       la.ln_beta = p.layer[l - 1].ln_b;
-      la.edges_in = pw.edges_out;
       la.dcand_hi = ws.dh.hi; la.dcand_lo = ws.dh.lo;
-      la.dedges_in = dedges[l % 2];
+      if (pw.dyn) {
+        la.edges_in = pw.edges_out;
+        la.dedges_in = dedges[l % 2];
+      } else {   // static edges are inputs: same masked view as the forward pass, no edge gradient
+        la.edges_in = ws.edges0;
+        for (int k = 0; k < 4; ++k) la.en[k] = powf(c.edge_enabled[k], (float)(l + 1));
+        la.dedges_in = nullptr;
+      }
     }
     la.dz = ws.dz;
-    if (lw.full) {
+    if (lw.dyn) {
       la.g = lw.g;
       la.edges_out = lw.edges_out;
       la.dedges_out = dedges[(l + 1) % 2];
@@ -96,7 +102,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     la.partials = partA;
     DRIN_TRY(gcn_layer_bwd(stream, la));
 
-    if (lw.full) {
+    if (lw.dyn) {
       // edge-update weights: fu = W_u xm + b_u, g = fu W_v, beta = fu . b_v
       GemmEpilogue ef;
       ef.C = ws.dfu; ef.ldc = D;
@@ -112,7 +118,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     MentionBwdArgs ma{};
     ma.B = c.batch; ma.D = D;
     ma.dxm = ws.dxm;
-    ma.dxu = lw.full ? ws.dxu : nullptr;
+    ma.dxu = lw.dyn ? ws.dxu : nullptr;
     if (l > 0) {
       ma.h_prev = ws.layer[l - 1].h;
       ma.ln_gamma = p.layer[l - 1].ln_w;

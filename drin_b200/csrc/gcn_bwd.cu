@@ -158,208 +158,7 @@ int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// gcn_layer_bwd
-// ---------------------------------------------------------------------------------------------
-// One candidate vertex row (entity text or entity image) of one mention.  e_mt / e_mi are the enabled
-// edge weights linking the row to the mention text / image vertex, ds_mt / ds_mi the gradients w.r.t. the
-// pre-sigmoid edge updates of those two edges (full layers).  Returns the four un-reduced dot products
-// needed for the edge gradients.
-template <int D, bool FULL>
-__device__ __forceinline__ void layer_bwd_row(const float* __restrict__ xrow, const float* __restrict__ dzrow, bool ln,
-                                              const float* s_gamma, const float* s_beta, const float* s_xmt,
-                                              const float* s_xmi, const float* s_dzmt, const float* s_dzmi,
-                                              const float* s_gmt, const float* s_gmi, float e_mt, float e_mi,
-                                              float ds_mt, float ds_mi, float invC, float invD, float* accA_mt,
-                                              float* accA_mi, float* accG_mt, float* accG_mi, float* p0, float* p1,
-                                              float* p2, float* pbias, bf16* out_hi, bf16* out_lo, int lane,
-                                              float& pd_mt, float& pd_mi, float& q_mt, float& q_mi) {
-  const bool has_dz = dzrow != nullptr;
-  RowT<D> x, d;
-  row_load<D>(x, xrow, lane);
-  if (has_dz) {
-    row_load<D>(d, dzrow, lane);
-  } else {
-#pragma unroll
-    for (int i = 0; i < RowT<D>::NV * 4; ++i) d.v[i] = 0.f;
-  }
-  RowT<D> xhat, dact;                                 // ln: normalised row and gelu'(y), computed once
-  float rstd = 0.f;
-  if (ln) {
-    xhat = x;
-    rstd = row_ln_gelu_recompute<D>(xhat, x, dact, s_gamma, s_beta, lane);   // x becomes the activated row
-  }
-  pd_mt = row_dot<D>(x, s_dzmt, lane);
-  pd_mi = FULL ? row_dot<D>(x, s_dzmi, lane) : 0.f;
-  q_mt = has_dz ? row_dot<D>(d, s_xmt, lane) : 0.f;
-  q_mi = has_dz ? row_dot<D>(d, s_xmi, lane) : 0.f;
-  const float ec_mt = e_mt * invC, ec_mi = e_mi * invC, dd_mt = ds_mt * invD, dd_mi = ds_mi * invD;
-#pragma unroll
-  for (int j = 0; j < RowT<D>::NV; ++j) {
-    const int off = (j * 32 + lane) * 4;
-    if (has_dz) {
-      float4 amt = *reinterpret_cast<float4*>(accA_mt + off);
-      float4 ami = *reinterpret_cast<float4*>(accA_mi + off);
-      amt.x += e_mt * d.v[4 * j]; amt.y += e_mt * d.v[4 * j + 1]; amt.z += e_mt * d.v[4 * j + 2]; amt.w += e_mt * d.v[4 * j + 3];
-      ami.x += e_mi * d.v[4 * j]; ami.y += e_mi * d.v[4 * j + 1]; ami.z += e_mi * d.v[4 * j + 2]; ami.w += e_mi * d.v[4 * j + 3];
-      *reinterpret_cast<float4*>(accA_mt + off) = amt;
-      *reinterpret_cast<float4*>(accA_mi + off) = ami;
-    }
-    const float4 zmt = *reinterpret_cast<const float4*>(s_dzmt + off);
-    d.v[4 * j] += ec_mt * zmt.x; d.v[4 * j + 1] += ec_mt * zmt.y; d.v[4 * j + 2] += ec_mt * zmt.z; d.v[4 * j + 3] += ec_mt * zmt.w;
-    if (FULL) {
-      const float4 zmi = *reinterpret_cast<const float4*>(s_dzmi + off);
-      const float4 gmt = *reinterpret_cast<const float4*>(s_gmt + off);
-      const float4 gmi = *reinterpret_cast<const float4*>(s_gmi + off);
-      float4 Gmt = *reinterpret_cast<float4*>(accG_mt + off);
-      float4 Gmi = *reinterpret_cast<float4*>(accG_mi + off);
-      Gmt.x += dd_mt * x.v[4 * j]; Gmt.y += dd_mt * x.v[4 * j + 1]; Gmt.z += dd_mt * x.v[4 * j + 2]; Gmt.w += dd_mt * x.v[4 * j + 3];
-      Gmi.x += dd_mi * x.v[4 * j]; Gmi.y += dd_mi * x.v[4 * j + 1]; Gmi.z += dd_mi * x.v[4 * j + 2]; Gmi.w += dd_mi * x.v[4 * j + 3];
-      *reinterpret_cast<float4*>(accG_mt + off) = Gmt;
-      *reinterpret_cast<float4*>(accG_mi + off) = Gmi;
-      d.v[4 * j] += ec_mi * zmi.x + dd_mt * gmt.x + dd_mi * gmi.x;
-      d.v[4 * j + 1] += ec_mi * zmi.y + dd_mt * gmt.y + dd_mi * gmi.y;
-      d.v[4 * j + 2] += ec_mi * zmi.z + dd_mt * gmt.z + dd_mi * gmi.z;
-      d.v[4 * j + 3] += ec_mi * zmi.w + dd_mt * gmt.w + dd_mi * gmi.w;
-    }
-  }
-  if (ln) {
-    row_ln_gelu_bwd_from<D>(xhat, dact, rstd, d, s_gamma, p0, p1, lane);
-    row_accum_smem<D>(d, p2, lane);
-  } else {
-    row_accum_smem<D>(d, pbias, lane);                // first layer: bias gradient of the input projection
-  }
-  row_store_planes<D>(d, out_hi, out_lo, lane);
-}
-
-template <int D, int NW, bool FULL>
-__global__ void __launch_bounds__(NW * 32, FULL ? 2 : 3) gcn_layer_bwd_kernel(const LayerBwdArgs a) {
-  extern __shared__ __align__(16) float sm[];
-  float* s_xmt = sm;                       // activated mention vertices of this layer
-  float* s_xmi = s_xmt + D;
-  float* s_dzmt = s_xmi + D;               // dL/dz of the mention text row
-  float* s_gamma = s_dzmt + D;
-  float* s_beta = s_gamma + D;
-  float* s_part = s_beta + D;              // [3][NW][D]
-  float* s_acc = s_part + 3 * NW * D;      // [2 or 4][NW][D]: A_mt, A_mi, (G_mt, G_mi)
-  float* s_gmt = s_acc + (FULL ? 4 : 2) * NW * D;   // g = fu W_v (FULL)
-  float* s_gmi = s_gmt + D;
-  float* s_dzmi = s_gmi + D;               // dL/dz of the mention image row (FULL; zero in the last layer)
-  float* s_db = s_dzmi + D;                // [2][NW] per-warp dbeta partials (FULL)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long B = a.B, BC = (long long)a.B * a.C;
-  const bool ln = a.ln_gamma != nullptr;
-  if (ln) {
-    for (int i = tid; i < D; i += NW * 32) {
-      s_gamma[i] = a.ln_gamma[i];
-      s_beta[i] = a.ln_beta[i];
-    }
-  }
-  for (int i = tid; i < 3 * NW * D; i += NW * 32) s_part[i] = 0.f;
-  float* p0 = s_part + (0 * NW + warp) * D;
-  float* p1 = s_part + (1 * NW + warp) * D;
-  float* p2 = s_part + (2 * NW + warp) * D;
-  float* accA_mt = s_acc + (0 * NW + warp) * D;
-  float* accA_mi = s_acc + (1 * NW + warp) * D;
-  float* accG_mt = FULL ? s_acc + (2 * NW + warp) * D : nullptr;
-  float* accG_mi = FULL ? s_acc + (3 * NW + warp) * D : nullptr;
-  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
-  // row offsets of the dz blocks for this layer's layout
-  const float* dz_mt = a.dz;
-  const float* dz_mi = FULL ? a.dz + B * D : nullptr;
-  const float* dz_et = a.dz + (FULL ? 2 * B : B) * D;
-  const float* dz_ei = FULL ? a.dz + (2 * B + BC) * D : nullptr;
-
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    __syncthreads();
-    for (int i = tid; i < D; i += NW * 32) {
-      s_xmt[i] = a.xm[(long long)b * D + i];
-      s_xmi[i] = a.xm[(B + b) * D + i];
-      s_dzmt[i] = dz_mt[(long long)b * D + i];
-      if (FULL) {
-        s_dzmi[i] = dz_mi[(long long)b * D + i];
-        s_gmt[i] = a.g[(long long)b * D + i];
-        s_gmi[i] = a.g[(B + b) * D + i];
-      }
-    }
-    row_zero_smem<D>(accA_mt, lane);
-    row_zero_smem<D>(accA_mi, lane);
-    if (FULL) {
-      row_zero_smem<D>(accG_mt, lane);
-      row_zero_smem<D>(accG_mi, lane);
-    }
-    float dbeta_mt = 0.f, dbeta_mi = 0.f;
-    __syncthreads();
-
-    for (int c = warp; c < a.C; c += NW) {
-      const long long r = (long long)b * a.C + c;
-      const float e0 = a.edges_in[r] * a.en[0], e1 = a.edges_in[BC + r] * a.en[1];
-      const float e2 = a.edges_in[2 * BC + r] * a.en[2], e3 = a.edges_in[3 * BC + r] * a.en[3];
-      float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
-      if (FULL) {   // through the sigmoid of the dynamic edge update
-        const float o0 = a.edges_out[r], o1 = a.edges_out[BC + r], o2 = a.edges_out[2 * BC + r], o3 = a.edges_out[3 * BC + r];
-        ds0 = a.dedges_out[r] * o0 * (1.f - o0);
-        ds1 = a.dedges_out[BC + r] * o1 * (1.f - o1);
-        ds2 = a.dedges_out[2 * BC + r] * o2 * (1.f - o2);
-        ds3 = a.dedges_out[3 * BC + r] * o3 * (1.f - o3);
-        dbeta_mt += (ds0 + ds1) * invD;
-        dbeta_mi += (ds2 + ds3) * invD;
-      }
-      const long long r_et = 2 * B + r, r_ei = 2 * B + BC + r;      // rows in the [mt; mi; et; ei] layout
-      float pd0, pd2, q0, q2, pd1, pd3, q1, q3;
-      layer_bwd_row<D, FULL>(a.x_et + r * D, dz_et + r * D, ln, s_gamma, s_beta, s_xmt, s_xmi, s_dzmt, s_dzmi, s_gmt,
-                             s_gmi, e0, e2, ds0, ds2, invC, invD, accA_mt, accA_mi, accG_mt, accG_mi, p0, p1, p2, p0,
-                             a.dcand_hi + r_et * D, a.dcand_lo ? a.dcand_lo + r_et * D : nullptr, lane, pd0, pd2, q0, q2);
-      layer_bwd_row<D, FULL>(a.x_ei + r * D, FULL ? dz_ei + r * D : nullptr, ln, s_gamma, s_beta, s_xmt, s_xmi, s_dzmt,
-                             s_dzmi, s_gmt, s_gmi, e1, e3, ds1, ds3, invC, invD, accA_mt, accA_mi, accG_mt, accG_mi, p0,
-                             p1, p2, p1, a.dcand_hi + r_ei * D, a.dcand_lo ? a.dcand_lo + r_ei * D : nullptr, lane, pd1,
-                             pd3, q1, q3);
-      if (a.dedges_in) {
-        pd0 = warp_sum(pd0); pd1 = warp_sum(pd1); pd2 = warp_sum(pd2); pd3 = warp_sum(pd3);
-        q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
-        if (lane == 0) {
-          a.dedges_in[r] = (pd0 * invC + q0 + ds0) * a.en[0];
-          a.dedges_in[BC + r] = (pd1 * invC + q1 + ds1) * a.en[1];
-          a.dedges_in[2 * BC + r] = (pd2 * invC + q2 + ds2) * a.en[2];
-          a.dedges_in[3 * BC + r] = (pd3 * invC + q3 + ds3) * a.en[3];
-        }
-      }
-    }
-    if (FULL && lane == 0) {
-      s_db[warp] = dbeta_mt;
-      s_db[NW + warp] = dbeta_mi;
-    }
-    __syncthreads();
-    // mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
-    for (int i = tid; i < 2 * D; i += NW * 32) {
-      const int which = i / D, col = i - which * D;
-      float t = which ? (FULL ? s_dzmi[col] : 0.f) : s_dzmt[col];
-#pragma unroll
-      for (int w = 0; w < NW; ++w) t += s_acc[(which * NW + w) * D + col];
-      a.dxm[(which ? B + b : (long long)b) * D + col] = t;
-      if (FULL) {
-        float gsum = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) gsum += s_acc[((2 + which) * NW + w) * D + col];
-        bf16 hh, ll;
-        split_bf16(gsum, hh, ll);
-        const long long gr = (which ? B + b : (long long)b) * D + col;
-        a.dg_hi[gr] = hh;
-        if (a.dg_lo) a.dg_lo[gr] = ll;
-      }
-    }
-    if (FULL && tid < 2) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) t += s_db[tid * NW + w];
-      a.dbeta[tid ? B + b : (long long)b] = t;
-    }
-  }
-  __syncthreads();
-  flush_partials<D, NW>(s_part, 3, a.partials, tid);
-}
-
-// ---------------------------------------------------------------------------------------------
-// gcn_layer_bwd, shared-memory staged version (default)
+// gcn_layer_bwd (shared-memory staged)
 // ---------------------------------------------------------------------------------------------
 // A producer warp streams chunks of BS_CH candidates (vertex rows + their dz rows + the mention-side
 // vectors) into a 2-stage ring with bulk async copies; BS_NW consumer warps alternate between
@@ -391,6 +190,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long B = a.B, BC = (long long)a.B * a.C;
   const bool ln = a.ln_gamma != nullptr;
+  const bool dyn = FULL && a.g != nullptr;               // dynamic edge update in this layer (false: static edges)
   const int nchunks = (a.C + BS_CH - 1) / BS_CH;
   auto full_bar = [&](int st) { return smem_u32(&bars[st]); };
   auto empty_bar = [&](int st) { return smem_u32(&bars[BS_STAGES + st]); };
@@ -425,7 +225,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
           const long long r0 = (long long)b * a.C + k * BS_CH;
           mbar_wait(empty_bar(stage), phase ^ 1u, nullptr, 0);
           const uint32_t rb = (uint32_t)(n * D * sizeof(float)), vb = D * (uint32_t)sizeof(float);
-          mbar_arrive_expect_tx(full_bar(stage), (FULL ? 4u : 3u) * rb + (FULL ? 6u : 3u) * vb);
+          mbar_arrive_expect_tx(full_bar(stage), (FULL ? 4u : 3u) * rb + (dyn ? 6u : (FULL ? 4u : 3u)) * vb);
           const uint32_t base = smem_u32(sm + stage * STAGE_FLOATS);
           const uint32_t arr = BS_CH * D * 4;
           bulk_copy_g2s(base, a.x_et + r0 * D, rb, full_bar(stage));
@@ -436,8 +236,8 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
           bulk_copy_g2s(v0, a.xm + (long long)b * D, vb, full_bar(stage));
           bulk_copy_g2s(v0 + vb, a.xm + (B + b) * D, vb, full_bar(stage));
           bulk_copy_g2s(v0 + 2 * vb, dz_mt + (long long)b * D, vb, full_bar(stage));
-          if (FULL) {
-            bulk_copy_g2s(v0 + 3 * vb, dz_mi + (long long)b * D, vb, full_bar(stage));
+          if (FULL) bulk_copy_g2s(v0 + 3 * vb, dz_mi + (long long)b * D, vb, full_bar(stage));
+          if (dyn) {
             bulk_copy_g2s(v0 + 4 * vb, a.g + (long long)b * D, vb, full_bar(stage));
             bulk_copy_g2s(v0 + 5 * vb, a.g + (B + b) * D, vb, full_bar(stage));
           }
@@ -480,7 +280,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
         sc[tid * 8 + 2] = a.edges_in[2 * BC + r] * a.en[2];
         sc[tid * 8 + 3] = a.edges_in[3 * BC + r] * a.en[3];
         float ds[4] = {0.f, 0.f, 0.f, 0.f};
-        if (FULL) {
+        if (dyn) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float o = a.edges_out[q * BC + r];
@@ -505,7 +305,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
           A_mt[0] += e1 * dzi0; A_mt[1] += e1 * dzi1;
           A_mi[0] += e3 * dzi0; A_mi[1] += e3 * dzi1;
           const float d0 = sc[c * 8 + 4] * invD, d1 = sc[c * 8 + 5] * invD, d2 = sc[c * 8 + 6] * invD, d3 = sc[c * 8 + 7] * invD;
-          if (!ln) {                                                            // layer-0 rows are already activated;
+          if (!ln && dyn) {                                                            // layer-0 rows are already activated;
             const float xe0 = Xet[c * D + col0], xe1 = Xet[c * D + col1];       // with a LayerNorm in front the
             const float xi0 = Xei[c * D + col0], xi1 = Xei[c * D + col1];       // g sums wait for column phase 2
             G_mt[0] += d0 * xe0 + d1 * xi0; G_mt[1] += d0 * xe1 + d1 * xi1;
@@ -553,12 +353,15 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
           d.v[4 * j] += ec_mt * zmt.x; d.v[4 * j + 1] += ec_mt * zmt.y; d.v[4 * j + 2] += ec_mt * zmt.z; d.v[4 * j + 3] += ec_mt * zmt.w;
           if (FULL) {
             const float4 zmi = *reinterpret_cast<const float4*>(s_dzmi + off);
-            const float4 gmt = *reinterpret_cast<const float4*>(s_gmt + off);
-            const float4 gmi = *reinterpret_cast<const float4*>(s_gmi + off);
-            d.v[4 * j] += ec_mi * zmi.x + dd_mt * gmt.x + dd_mi * gmi.x;
-            d.v[4 * j + 1] += ec_mi * zmi.y + dd_mt * gmt.y + dd_mi * gmi.y;
-            d.v[4 * j + 2] += ec_mi * zmi.z + dd_mt * gmt.z + dd_mi * gmi.z;
-            d.v[4 * j + 3] += ec_mi * zmi.w + dd_mt * gmt.w + dd_mi * gmi.w;
+            d.v[4 * j] += ec_mi * zmi.x; d.v[4 * j + 1] += ec_mi * zmi.y; d.v[4 * j + 2] += ec_mi * zmi.z; d.v[4 * j + 3] += ec_mi * zmi.w;
+            if (dyn) {
+              const float4 gmt = *reinterpret_cast<const float4*>(s_gmt + off);
+              const float4 gmi = *reinterpret_cast<const float4*>(s_gmi + off);
+              d.v[4 * j] += dd_mt * gmt.x + dd_mi * gmi.x;
+              d.v[4 * j + 1] += dd_mt * gmt.y + dd_mi * gmi.y;
+              d.v[4 * j + 2] += dd_mt * gmt.z + dd_mi * gmi.z;
+              d.v[4 * j + 3] += dd_mt * gmt.w + dd_mi * gmi.w;
+            }
           }
         }
         const long long orow = (kind ? 2 * B + BC : 2 * B) + r0 + c;      // row in the [mt; mi; et; ei] layout
@@ -623,7 +426,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
             part[1][0] += dy0; part[1][1] += dy1;                                   // dbeta (LayerNorm)
             part[2][0] += rstd * (g0 * dy0 - m1 - xh0 * m2);                        // db_h = sum dL/dh
             part[2][1] += rstd * (g1 * dy1 - m1 - xh1 * m2);
-            if (FULL) {   // middle layers (L >= 3): g sums need the activated vertex, recomputed from xhat
+            if (dyn) {    // middle layers (L >= 3): g sums need the activated vertex, recomputed from xhat
               const float a0 = gelu_f(fmaf(xh0, g0, s_beta[col0])), a1 = gelu_f(fmaf(xh1, g1, s_beta[col1]));
               const float dm = sc[c * 8 + 4 + kind] * invD, di = sc[c * 8 + 6 + kind] * invD;   // edges (mt,row), (mi,row)
               G_mt[0] += dm * a0; G_mt[1] += dm * a1;
@@ -643,7 +446,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
         a.dxm[(long long)b * D + col1] = s_dzmt[col1] + A_mt[1];
         a.dxm[(B + b) * D + col0] = (FULL ? s_dzmi[col0] : 0.f) + A_mi[0];
         a.dxm[(B + b) * D + col1] = (FULL ? s_dzmi[col1] : 0.f) + A_mi[1];
-        if (FULL) {
+        if (dyn) {
           bf16 h, l;
           split_bf16(G_mt[0], h, l);
           a.dg_hi[(long long)b * D + col0] = h; if (a.dg_lo) a.dg_lo[(long long)b * D + col0] = l;
@@ -677,40 +480,18 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
   }
 }
 
-static bool bwd_use_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DRIN_BWD_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
-  if (!bwd_use_v1()) {
-    // persistent: every CTA of the fixed partial-sum grid must write its partials, so launch all BW_CTAS CTAs
-    const size_t smem = (size_t)(BS_STAGES * (4 * BS_CH + 6) * D + 2 * D + 2 * BS_CH * 8 + 2 * BS_CH * 8) * sizeof(float);
-    if (a.full) {
-      DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_stream_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gcn_layer_bwd_stream_kernel<D, true><<<BS_GRID, BS_THREADS, smem, stream>>>(a);
-    } else {
-      DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_stream_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gcn_layer_bwd_stream_kernel<D, false><<<BS_GRID, BS_THREADS, smem, stream>>>(a);
-    }
-    DRIN_LAUNCH_CHECK();
-    return DRIN_OK;
-  }
+  // persistent: every CTA of the fixed partial-sum grid writes its partials
+  const size_t smem = (size_t)(BS_STAGES * (4 * BS_CH + 6) * D + 2 * D + 2 * BS_CH * 8 + 2 * BS_CH * 8) * sizeof(float);
   if (a.full) {
-    const size_t smem = (size_t)(8 + 7 * BW_NW) * D * sizeof(float) + 2 * BW_NW * sizeof(float);
-    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gcn_layer_bwd_kernel<D, BW_NW, true><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_stream_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcn_layer_bwd_stream_kernel<D, true><<<BS_GRID, BS_THREADS, smem, stream>>>(a);
   } else {
-    const size_t smem = (size_t)(5 + 5 * BW_NW) * D * sizeof(float);
-    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_kernel<D, BW_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gcn_layer_bwd_kernel<D, BW_NW, false><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_stream_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcn_layer_bwd_stream_kernel<D, false><<<BS_GRID, BS_THREADS, smem, stream>>>(a);
   }
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
@@ -860,6 +641,6 @@ int colsum_reduce(cudaStream_t stream, const float* src0, int ctas0, const float
 }
 
 int backward_ctas() { return BW_CTAS; }
-int layer_bwd_ctas() { return bwd_use_v1() ? BW_CTAS : BS_GRID; }
+int layer_bwd_ctas() { return BS_GRID; }
 
 }  // namespace drin

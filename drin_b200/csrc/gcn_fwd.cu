@@ -83,6 +83,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const L
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long B = a.B, BC = (long long)a.B * a.C;
   const bool ln = a.ln_gamma != nullptr;
+  const bool dyn = FULL && a.g != nullptr;                    // dynamic edge update (false: static edges)
   const int nchunks = (a.C + ST_CH - 1) / ST_CH;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[ST_STAGES + s]); };
@@ -113,14 +114,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const L
           const long long r0 = (long long)b * a.C + k * ST_CH;
           mbar_wait(empty_bar(stage), phase ^ 1u, nullptr, 0);
           const uint32_t row_bytes = (uint32_t)(n * D * sizeof(float));
-          mbar_arrive_expect_tx(full_bar(stage), 2 * row_bytes + NVEC * D * (uint32_t)sizeof(float));
+          mbar_arrive_expect_tx(full_bar(stage), 2 * row_bytes + (dyn ? 4u : 2u) * D * (uint32_t)sizeof(float));
           const uint32_t base = smem_u32(sm + stage * STAGE_FLOATS);
           bulk_copy_g2s(base, a.x_et + r0 * D, row_bytes, full_bar(stage));
           bulk_copy_g2s(base + ST_CH * D * 4, a.x_ei + r0 * D, row_bytes, full_bar(stage));
           const uint32_t vb = base + 2 * ST_CH * D * 4;
           bulk_copy_g2s(vb, a.xm + (long long)b * D, D * 4, full_bar(stage));
           bulk_copy_g2s(vb + D * 4, a.xm + (B + b) * D, D * 4, full_bar(stage));
-          if (FULL) {
+          if (dyn) {
             bulk_copy_g2s(vb + 2 * D * 4, a.g + (long long)b * D, D * 4, full_bar(stage));
             bulk_copy_g2s(vb + 3 * D * 4, a.g + (B + b) * D, D * 4, full_bar(stage));
           }
@@ -143,8 +144,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const L
       *reinterpret_cast<float4*>(acc_mt + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(acc_mi + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float beta_mt = FULL ? a.beta_u[b] : 0.f;
-    const float beta_mi = FULL ? a.beta_u[B + b] : 0.f;
+    const float beta_mt = dyn ? a.beta_u[b] : 0.f;
+    const float beta_mi = dyn ? a.beta_u[B + b] : 0.f;
     for (int k = 0; k < nchunks; ++k) {
       const int n = min(ST_CH, a.C - k * ST_CH);
       mbar_wait(full_bar(stage), phase, nullptr, 0);
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const L
           row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
           row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
         }
-        if (FULL) {
+        if (dyn) {
           d0 = row_dot<D>(xet, s_gmt, lane); d1 = row_dot<D>(xei, s_gmt, lane);
           d2 = row_dot<D>(xet, s_gmi, lane); d3 = row_dot<D>(xei, s_gmi, lane);
         }
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const L
         }
         row_store_planes<D>(xet, a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane);
         if (FULL) row_store_planes<D>(xei, a.z_hi + zr_ei * D, a.z_lo ? a.z_lo + zr_ei * D : nullptr, lane);
-        if (FULL) {
+        if (dyn) {
           // dynamic edge update (model.py:131-134,148-153): e' = sigmoid((v . g_u + fu . b_v) / D + e)
           d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
           if (lane == 0) {

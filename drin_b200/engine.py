@@ -57,11 +57,12 @@ def param_shapes(num_layers: int, D: int = 768, R: int = 2048) -> Dict[str, Tupl
     return shapes
 
 
-def dead_param_keys(num_layers: int) -> List[str]:
+def dead_param_keys(num_layers: int, static_edges: bool = False) -> List[str]:
     """Parameters that never receive a gradient in the reference (grad is None): the edge update of the
-    last GCN layer is dead code (drin/model.py:131-134)."""
-    l = num_layers - 1
-    return [f"gcn_layers.{l}.{s}" for s in ("w_u.weight", "w_u.bias", "w_v.weight", "w_v.bias")]
+    last GCN layer is dead code (drin/model.py:131-134); with gcn_edge_type="static" no layer
+    runs an edge update (model.py:135-136)."""
+    layers = range(num_layers) if static_edges else (num_layers - 1,)
+    return [f"gcn_layers.{l}.{s}" for l in layers for s in ("w_u.weight", "w_u.bias", "w_v.weight", "w_v.bias")]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -171,9 +172,10 @@ def inspect_batch(batch: Sequence[torch.Tensor], num_candidates_model: Optional[
 class Engine:
     """One instance per module: caches the workspace and marshals calls into the C ABI."""
 
-    def __init__(self, num_layers: int, edge_enabled: Sequence[float] = (1, 1, 1, 1)):
+    def __init__(self, num_layers: int, edge_enabled: Sequence[float] = (1, 1, 1, 1), static_edges: bool = False):
         self.lib = _lib.load()
         self.num_layers = int(num_layers)
+        self.static_edges = bool(static_edges)
         self.edge_enabled = tuple(float(x) for x in edge_enabled)
         if len(self.edge_enabled) != 4:
             raise ValueError("gcn_edge_enabled must have 4 entries")
@@ -188,6 +190,7 @@ class Engine:
         cfg.precision, cfg.training = pb.precision, int(training)
         for i in range(4):
             cfg.edge_enabled[i] = self.edge_enabled[i]
+        cfg.static_edges = int(self.static_edges)
         return cfg
 
     @staticmethod

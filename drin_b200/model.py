@@ -43,15 +43,17 @@ def _read_args(overrides: dict) -> dict:
 
 
 def _check_supported(cfg: dict) -> None:
-    want = dict(gcn_edge_type="dynamic", gcn_edge_feature="scaler", gcn_vertex_activation="gelu",
+    want = dict(gcn_edge_feature="scaler", gcn_vertex_activation="gelu",
                 gcn_edge_activation="sigmoid", mention_final_layer_name="linear",
                 mention_final_representation="avg extract", entity_final_layer_name="linear",
                 entity_final_pooling="avg", online_bert=False)
     bad = {k: cfg[k] for k, v in want.items() if cfg[k] != v}
+    if cfg["gcn_edge_type"] not in ("dynamic", "static"):
+        bad["gcn_edge_type"] = cfg["gcn_edge_type"]
     if bad:
         raise NotImplementedError(
-            f"drin_b200 implements the default DRIN configuration only; unsupported settings: {bad} "
-            "(ablation variants are listed as 'next' in SURVEY.md section 8f)")
+            f"drin_b200 implements scalar-edge DRIN (dynamic or static edges, any layer count / edge mask); "
+            f"unsupported settings: {bad} (see SURVEY.md section 8f)")
     if cfg["gcn_embed_dim"] != 768 or cfg["bert_embed_dim"] != 768:
         raise NotImplementedError("kernels are built for gcn_embed_dim = bert_embed_dim = 768")
     if cfg["mention_final_output_dim"] != cfg["gcn_embed_dim"] or cfg["entity_final_output_dim"] != cfg["gcn_embed_dim"]:
@@ -135,7 +137,8 @@ class Model(nn.Module):
         self.gcn_layers = nn.ModuleList([_GCNLayer(D) for _ in range(self.num_gcn_layers)])
         self._param_names: List[str] = [n for n, _ in self.named_parameters()]
         assert self._param_names == E.param_keys(self.num_gcn_layers), "state_dict keys drifted from the reference"
-        self._dead = E.dead_param_keys(self.num_gcn_layers)
+        self.static_edges = cfg["gcn_edge_type"] == "static"
+        self._dead = E.dead_param_keys(self.num_gcn_layers, self.static_edges)
         self._engine_obj: Optional[E.Engine] = None
         self._flat: Optional[torch.Tensor] = None
         self._flat_grad: Optional[torch.Tensor] = None
@@ -192,7 +195,7 @@ class Model(nn.Module):
     @property
     def _engine(self) -> E.Engine:
         if self._engine_obj is None:
-            self._engine_obj = E.Engine(self.num_gcn_layers, self.cfg["gcn_edge_enabled"])
+            self._engine_obj = E.Engine(self.num_gcn_layers, self.cfg["gcn_edge_enabled"], self.static_edges)
         return self._engine_obj
 
     # ---- the reference's forward signature (drin/model.py:164) ----------------------------------

@@ -48,6 +48,9 @@ typedef struct drin_config {
   int32_t precision;        /* enum drin_precision                                        */
   int32_t training;         /* 1: keep what drin_backward needs in the workspace          */
   float edge_enabled[4];    /* gcn_edge_enabled, order tt, ti, it, ii                     */
+  int32_t static_edges;     /* 0: gcn_edge_type "dynamic" (learned edge update, model.py:130-134);
+                               1: "static" (masked edges pass through, model.py:135-136; w_u / w_v of every
+                               layer receive no gradient)                                  */
 } drin_config;
 
 /* The 14 model inputs in the order of drin/model.py:164-180 (= drin/data.py:110-125).  Feature tensors

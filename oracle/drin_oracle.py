@@ -57,6 +57,7 @@ class DrinConfig:
     bert_embed_dim: int = 768                # args.py:45
     resnet_embed_dim: int = 2048             # args.py:52
     gcn_edge_enabled: Tuple[float, ...] = (1, 1, 1, 1)   # args.py:34
+    gcn_edge_type: str = "dynamic"           # args.py:32 ("dynamic" | "static")
     triplet_margin: float = 0.25             # args.py:117,125
 
 
@@ -172,7 +173,7 @@ def edge_encode(batch, loops=False) -> Tuple[Tensor, Tensor]:
 
 
 def gcn_layer(sd, layer: int, cfg: DrinConfig, V: List[Tensor], E: List[Tensor]):
-    """GCNLayer.forward for the default scalar/dynamic configuration, drin/model.py:121-153."""
+    """GCNLayer.forward for scalar edges (dynamic or static edge type), drin/model.py:121-153."""
     k = gcn_keys(layer)
     mt, mi, et, ei = V
     C = et.shape[1]
@@ -189,6 +190,8 @@ def gcn_layer(sd, layer: int, cfg: DrinConfig, V: List[Tensor], E: List[Tensor])
         return F.gelu(F.layer_norm(h, (h.shape[-1],), sd[k["ln_w"]], sd[k["ln_b"]], 1e-5))
 
     newV = [upd(a_mt, mt), upd(a_mi, mi), upd(a_et, et), upd(a_ei, ei)]
+    if cfg.gcn_edge_type != "dynamic":                                # model.py:135-136: the MASKED edges pass through
+        return newV, E
     # model.py:104,131-134,148-153: e' = sigmoid(mean_D(W_u u * W_v v) + e)
     fu = {0: F.linear(mt, sd[k["w_u"]], sd[k["b_u"]]), 1: F.linear(mi, sd[k["w_u"]], sd[k["b_u"]])}
     fv = {2: F.linear(et, sd[k["w_v"]], sd[k["b_v"]]), 3: F.linear(ei, sd[k["w_v"]], sd[k["b_v"]])}

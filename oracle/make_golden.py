@@ -41,6 +41,10 @@ CASES = [
          overrides=dict(triplet_margin=0.05)),
     dict(name="wd_b8_layers3", dataset="wikidiverse", B=8, cands=10, seed=8, weights="spread",
          overrides=dict(num_gcn_layers=3)),
+    dict(name="wd_b8_static", dataset="wikidiverse", B=8, cands=10, seed=10, weights="spread",
+         overrides=dict(gcn_edge_type="static")),
+    dict(name="wd_b6_static_l3_mask", dataset="wikidiverse", B=6, cands=10, seed=11, weights="spread",
+         overrides=dict(gcn_edge_type="static", num_gcn_layers=3, gcn_edge_enabled=[1, 1, 0, 1])),
 ]
 
 
@@ -56,6 +60,7 @@ def run_case(case):
     cfg = O.DrinConfig(num_candidates_model=case["cands"] + 1,
                        num_gcn_layers=ov.get("num_gcn_layers", 2),
                        gcn_edge_enabled=tuple(ov.get("gcn_edge_enabled", (1, 1, 1, 1))),
+                       gcn_edge_type=ov.get("gcn_edge_type", "dynamic"),
                        triplet_margin=ov.get("triplet_margin", 0.25))
     batch = make_batch(case["dataset"], case["B"], case["seed"], case["cands"], **case.get("batch_kw", {}))
     sd = O.init_state(cfg, seed=0)
@@ -132,8 +137,12 @@ def loss_cases():
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    torch.save(loss_cases(), os.path.join(out_dir, "triplet_loss_cases.pt"))
+    only = set(sys.argv[1:])            # optional: regenerate only the named cases
+    if not only:
+        torch.save(loss_cases(), os.path.join(out_dir, "triplet_loss_cases.pt"))
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         fx = run_case(case)
         path = os.path.join(out_dir, case["name"] + ".pt")
         torch.save(fx, path)

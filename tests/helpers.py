@@ -22,6 +22,7 @@ def load_case(path):
     cfg = O.DrinConfig(num_candidates_model=case["cands"] + 1,
                        num_gcn_layers=ov.get("num_gcn_layers", 2),
                        gcn_edge_enabled=tuple(ov.get("gcn_edge_enabled", (1, 1, 1, 1))),
+                       gcn_edge_type=ov.get("gcn_edge_type", "dynamic"),
                        triplet_margin=ov.get("triplet_margin", 0.25))
     batch = make_batch(case["dataset"], case["B"], case["seed"], case["cands"], **case.get("batch_kw", {}))
     sd = O.init_state(cfg, seed=0)

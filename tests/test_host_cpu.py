@@ -54,7 +54,7 @@ def test_model_is_a_drop_in_for_the_reference_constructor():
 
 
 def test_unsupported_configurations_fail_loudly():
-    for kw in (dict(gcn_edge_feature="vector"), dict(gcn_edge_type="static"), dict(gcn_vertex_activation="relu"),
+    for kw in (dict(gcn_edge_feature="vector"), dict(gcn_edge_type="learned"), dict(gcn_vertex_activation="relu"),
                dict(gcn_embed_dim=512)):
         with pytest.raises(NotImplementedError):
             drin_b200.Model(**kw)
@@ -81,3 +81,6 @@ def test_param_key_tables():
     assert E.param_keys(2) == O.state_dict_keys(O.DrinConfig())
     assert E.dead_param_keys(2) == ["gcn_layers.1.w_u.weight", "gcn_layers.1.w_u.bias",
                                     "gcn_layers.1.w_v.weight", "gcn_layers.1.w_v.bias"]
+    # gcn_edge_type="static": no layer has an edge update (drin/model.py:135-136)
+    assert len(E.dead_param_keys(3, static_edges=True)) == 12
+    assert int(drin_b200.Model(gcn_edge_type="static").dead_mask().sum()) == 4 * (768 * 768 + 768)
