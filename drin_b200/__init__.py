@@ -7,8 +7,10 @@ from .model import Model  # noqa: F401
 from .loss import TripletLoss, TopkAccuracy  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .trainer import HostFeeder, Trainer  # noqa: F401
+from .store import FeatureStore, IndexedBatch  # noqa: F401
 
-__all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "HostFeeder", "install_as_reference_module"]
+__all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "HostFeeder", "FeatureStore", "IndexedBatch",
+           "install_as_reference_module"]
 
 
 def install_as_reference_module() -> None:

@@ -22,7 +22,7 @@ class DrinConfig(C.Structure):
         ("batch", c_int32), ("candidates", c_int32), ("mention_tokens", c_int32), ("entity_tokens", c_int32),
         ("regions", c_int32), ("mention_objects", c_int32), ("entity_objects", c_int32), ("embed_dim", c_int32),
         ("resnet_dim", c_int32), ("gcn_layers", c_int32), ("precision", c_int32), ("training", c_int32),
-        ("edge_enabled", c_float * 4), ("static_edges", c_int32),
+        ("edge_enabled", c_float * 4), ("static_edges", c_int32), ("indexed", c_int32),
     ]
 
 
@@ -31,7 +31,7 @@ class DrinInputs(C.Structure):
         "mention_text_feature", "mention_text_mask", "mention_start_pos", "mention_end_pos",
         "mention_image_feature", "mention_object_feature", "mention_object_score", "entity_text_feature",
         "entity_text_mask", "entity_image_feature", "entity_object_feature", "entity_object_score",
-        "miet_similarity", "mtei_similarity")]
+        "miet_similarity", "mtei_similarity", "mention_index", "entity_index")]
 
 
 class DrinLayerParams(C.Structure):

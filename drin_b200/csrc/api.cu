@@ -99,6 +99,10 @@ int drin_frontend(const drin_config* cfg, const drin_inputs* in, float* span, fl
   fa.emask = (const long long*)in->entity_text_mask; fa.eif = in->entity_image_feature;
   fa.eof = in->entity_object_feature; fa.eos = in->entity_object_score; fa.miet = in->miet_similarity;
   fa.mtei = in->mtei_similarity;
+  if (c.indexed) {
+    fa.mention_index = (const long long*)in->mention_index;
+    fa.entity_index = (const long long*)in->entity_index;
+  }
   fa.span_f = span; fa.mim_f = mimean; fa.ep_f = epool; fa.edges = edges;
   return frontend((cudaStream_t)stream, fa, c.precision == DRIN_BF16);
 }

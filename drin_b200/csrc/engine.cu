@@ -47,13 +47,13 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
   ws.w_ei = m.planes(D * R, split);
   ws.span = m.planes(B * D, split);
   ws.mim = m.planes(B * R, split);
-  if (split || c.entity_tokens > 0) {
+  if (split || c.entity_tokens > 0 || c.indexed) {
     ws.epool = m.planes(BC * D, split);
   } else {   // bf16 WikiDiverse: the entity text rows are the GEMM operand as they are
     ws.epool = Planes();
     if (in) ws.epool.hi = const_cast<bf16*>(static_cast<const bf16*>(in->entity_text_feature));
   }
-  if (split) {
+  if (split || c.indexed) {
     ws.eimg = m.planes(BC * R, split);
   } else {
     ws.eimg = Planes();
@@ -161,10 +161,18 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
   fa.emask = (const long long*)in.entity_text_mask; fa.eif = in.entity_image_feature;
   fa.eof = in.entity_object_feature; fa.eos = in.entity_object_score; fa.miet = in.miet_similarity;
   fa.mtei = in.mtei_similarity;
+  if (c.indexed) {
+    if (!in.mention_index) return fail(DRIN_ERR_ARG, "indexed inputs need drin_inputs.mention_index");
+    if (c.entity_tokens > 0 && !in.entity_index)
+      return fail(DRIN_ERR_ARG, "indexed WikiMEL-layout inputs need drin_inputs.entity_index (entity tables are per entity)");
+    fa.mention_index = (const long long*)in.mention_index;
+    fa.entity_index = (const long long*)in.entity_index;
+  }
   fa.span_hi = ws.span.hi; fa.span_lo = ws.span.lo; fa.mim_hi = ws.mim.hi; fa.mim_lo = ws.mim.lo;
-  const bool own_epool = !bf16_in || c.entity_tokens > 0;
+  const bool own_epool = !bf16_in || c.entity_tokens > 0 || c.indexed;
+  const bool own_eimg = !bf16_in || c.indexed;
   fa.ep_hi = own_epool ? ws.epool.hi : nullptr; fa.ep_lo = own_epool ? ws.epool.lo : nullptr;
-  fa.ei_hi = bf16_in ? nullptr : ws.eimg.hi; fa.ei_lo = bf16_in ? nullptr : ws.eimg.lo;
+  fa.ei_hi = own_eimg ? ws.eimg.hi : nullptr; fa.ei_lo = own_eimg ? ws.eimg.lo : nullptr;
   fa.edges = ws.edges0;
   DRIN_TRY(frontend(stream, fa, bf16_in));
 

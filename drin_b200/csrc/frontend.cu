@@ -100,9 +100,11 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = (int)(item / S), slice = (int)(item - (long long)b * S);
     const bool owner = slice == 0;
+    // table row of this mention (drin/data.py:99-108 done on device when the inputs are resident tables)
+    const long long m = a.mention_index ? a.mention_index[b] : (long long)b;
     // ------------------------------ phase A: mention side ------------------------------
     // span mean (ghmfc.py:55-60): rows start..end-1 with Python slice clamping
-    long long s = a.start[b], e = a.end[b];
+    long long s = a.start[m], e = a.end[m];
     if (s < 0) s += a.Lm;
     if (e < 0) e += a.Lm;
     s = s < 0 ? 0 : (s > a.Lm ? a.Lm : s);
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
       float acc[VN];
 #pragma unroll
       for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-      const T* base = mtf + (long long)b * a.Lm * D + v * VN;
+      const T* base = mtf + m * a.Lm * D + v * VN;
       long long r = s;
       for (; r + 4 <= e; r += 4) {
         float f[4][VN];
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
       float part = 0.f;
       for (int v = tid; v < R / VN; v += NW * 32) {
         float f[VN];
-        Vec<T>::load(mof + ((long long)b * a.Om + o) * R + v * VN, f);
+        Vec<T>::load(mof + (m * a.Om + o) * R + v * VN, f);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
           s_mo[o * R + v * VN + i] = f[i];
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
         float acc[VN];
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-        const T* base = mif + (long long)b * a.P * R + v * VN;
+        const T* base = mif + m * a.P * R + v * VN;
         int r = 0;
         for (; r + 7 <= a.P; r += 7) {
           float f[7][VN];
@@ -205,18 +207,20 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
       float t = 0.f;
       for (int w = 0; w < NW; ++w) t += s_red[NW * (1 + o) + w];
       s_mo_norm[o] = fmaxf(sqrtf(t), 1e-8f);
-      s_ms[o] = a.mos[(long long)b * a.Om + o];
+      s_ms[o] = a.mos[m * a.Om + o];
     }
     __syncthreads();
 
     // ------------------------------ phase B: one warp per candidate ------------------------------
     const int c_end = min(a.C, (slice + 1) * cps);
     for (int c = slice * cps + warp; c < c_end; c += NW) {
-      const long long r = (long long)b * a.C + c;
+      const long long r = (long long)b * a.C + c;         // output row
+      const long long rm = m * a.C + c;                   // row in the mention-major [N, C] tables (CLIP similarities)
+      const long long re = a.entity_index ? a.entity_index[r] : rm;   // row in the entity-side tables
       // all rows of the candidate that do not depend on anything are requested up front
       float eo[RV][VN], ec[DV][VN];
-      load_row_tile<T, RV>(eof + r * a.Oe * R, lane, eo);                       // first entity object crop
-      load_row_tile<T, DV>(etf + (a.Le ? r * (long long)a.Le * D : r * D), lane, ec);   // CLS row / pooled row
+      load_row_tile<T, RV>(eof + re * a.Oe * R, lane, eo);                      // first entity object crop
+      load_row_tile<T, DV>(etf + (a.Le ? re * (long long)a.Le * D : re * D), lane, ec);   // CLS row / pooled row
 
       // --- entity text: tt = cos(span, CLS) and the pooled vertex feature (ghmfc.py:237-249, model.py:73-76)
       float dot = 0.f, nrm = 0.f;
@@ -241,14 +245,14 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
         }
       } else {
         long long n = 0;
-        for (int t = lane; t < a.Le; t += 32) n += a.emask[r * a.Le + t];
+        for (int t = lane; t < a.Le; t += 32) n += a.emask[re * a.Le + t];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
         long long t0 = 1, t1 = n - 1;                       // tokens 1 .. n-2 (drops CLS and SEP)
         if (t1 < 0) t1 += a.Le;                             // Python slice semantics for a negative stop
         if (t1 > a.Le) t1 = a.Le;
         const float cnt_e = t1 > t0 ? (float)(t1 - t0) : 0.f;
-        const T* rowbase = etf + r * (long long)a.Le * D;
+        const T* rowbase = etf + re * (long long)a.Le * D;
         float acc[DV][VN];
 #pragma unroll
         for (int v = 0; v < DV; ++v)
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
       // --- object crops: ii (model.py:84-92)
       float sim = 0.f, den = 0.f;
       for (int j = 0; j < a.Oe; ++j) {
-        if (j > 0) load_row_tile<T, RV>(eof + (r * a.Oe + j) * R, lane, eo);
+        if (j > 0) load_row_tile<T, RV>(eof + (re * a.Oe + j) * R, lane, eo);
         float d[FE_MAX_OM] = {0.f, 0.f, 0.f, 0.f};
         float en2 = 0.f;
 #pragma unroll
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
         }
         en2 = warp_sum(en2);
         const float enorm = fmaxf(sqrtf(en2), 1e-8f);
-        const float es = a.eos[r * a.Oe + j];
+        const float es = a.eos[re * a.Oe + j];
         for (int o = 0; o < a.Om; ++o) {                    // upstream loop order: i (mention) outer, j inner;
           const float cs = warp_sum(d[o]) / (s_mo_norm[o] * enorm);   // with Oe == 1 the orders coincide
           const float w = s_ms[o] * es;
@@ -322,14 +326,14 @@ __global__ void __launch_bounds__(NW * 32, 3) frontend_kernel(const FrontendArgs
 
       // --- entity image row -> planes (A operand of the entity-image projection, model.py:45)
       if (a.ei_hi) {
-        load_row_tile<T, RV>(eif + r * R, lane, eo);
+        load_row_tile<T, RV>(eif + re * R, lane, eo);
 #pragma unroll
         for (int v = 0; v < RV; ++v) store_planes<VN>(a.ei_hi, a.ei_lo, r * R + (v * 32 + lane) * VN, eo[v]);
       }
       if (lane == 0 && a.edges) {                            // model.py:201-204 order tt, ti, it, ii
         a.edges[r] = tt;
-        a.edges[BC + r] = a.mtei[r] / 100.f;
-        a.edges[2 * BC + r] = a.miet[r] / 100.f;
+        a.edges[BC + r] = a.mtei[rm] / 100.f;
+        a.edges[2 * BC + r] = a.miet[rm] / 100.f;
         a.edges[3 * BC + r] = ii;
       }
     }

@@ -32,6 +32,8 @@ struct FrontendArgs {
   const void* mif; const void* mof; const float* mos;
   const void* etf; const long long* emask; const void* eif; const void* eof; const float* eos;
   const float* miet; const float* mtei;
+  const long long* mention_index;   // [B] or null: table row of mention b (null: b)
+  const long long* entity_index;    // [B, C] or null: entity-table row of candidate (b, c) (null: m * C + c)
   // outputs (any may be null)
   bf16 *span_hi, *span_lo;       // [B, D]
   bf16 *mim_hi, *mim_lo;         // [B, R]

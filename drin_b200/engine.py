@@ -182,7 +182,7 @@ class Engine:
         self._ws: Optional[torch.Tensor] = None
 
     # ---- struct marshalling -----------------------------------------------------------------
-    def config(self, pb: Problem, training: bool) -> _lib.DrinConfig:
+    def config(self, pb: Problem, training: bool, indexed: bool = False) -> _lib.DrinConfig:
         cfg = _lib.DrinConfig()
         cfg.batch, cfg.candidates, cfg.mention_tokens, cfg.entity_tokens = pb.B, pb.C, pb.Lm, pb.Le
         cfg.regions, cfg.mention_objects, cfg.entity_objects = pb.P, pb.Om, pb.Oe
@@ -191,13 +191,19 @@ class Engine:
         for i in range(4):
             cfg.edge_enabled[i] = self.edge_enabled[i]
         cfg.static_edges = int(self.static_edges)
+        cfg.indexed = int(indexed)
         return cfg
 
     @staticmethod
-    def inputs(batch: Sequence[torch.Tensor]) -> _lib.DrinInputs:
+    def inputs(batch) -> _lib.DrinInputs:
+        """batch: the 14 tensors of one batch, or a store.IndexedBatch (resident tables + row indices)."""
         s = _lib.DrinInputs()
-        for name, t in zip(INPUT_NAMES, batch):
+        indexed = hasattr(batch, "mention_index")
+        for name, t in zip(INPUT_NAMES, batch.tables if indexed else batch):
             setattr(s, name, t.data_ptr())
+        if indexed:
+            s.mention_index = batch.mention_index.data_ptr()
+            s.entity_index = 0 if batch.entity_index is None else batch.entity_index.data_ptr()
         return s
 
     def params(self, tensors: Dict[str, torch.Tensor], D: int, R: int) -> _lib.DrinParams:
@@ -239,9 +245,18 @@ class Engine:
     # ---- calls ------------------------------------------------------------------------------
     def forward(self, batch, params: Dict[str, torch.Tensor], training: bool,
                 num_candidates_model: Optional[int] = None):
-        pb = inspect_batch(batch, num_candidates_model)
-        cfg = self.config(pb, training)
-        dev = batch[0].device
+        indexed = hasattr(batch, "mention_index")
+        if indexed:
+            pb = batch.problem()
+            if num_candidates_model is not None and pb.C != num_candidates_model:
+                raise RuntimeError(f"store has {pb.C} candidate slots but num_candidates_model = {num_candidates_model}")
+            if not batch.mention_index.is_cuda:
+                raise RuntimeError("the feature store must live on a CUDA device (no CPU fallback in drin_b200)")
+            dev = batch.mention_index.device
+        else:
+            pb = inspect_batch(batch, num_candidates_model)
+            dev = batch[0].device
+        cfg = self.config(pb, training, indexed)
         with torch.cuda.device(dev):
             ws = self.workspace(cfg, dev)
             scores = torch.empty(pb.B, pb.C, dtype=torch.float32, device=dev)

@@ -52,10 +52,13 @@ class Trainer:
         return dist.get_world_size(self.group) if _dist_on(self.group) else 1
 
     def forward_backward(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:
-        """batch: the loader's 15-tuple (14 inputs + uint8 labels), local shard.  Leaves summed gradients in
-        model.flat_grads and returns the global loss (device scalar)."""
+        """batch: the loader's 15-tuple (14 inputs + uint8 labels) or a ``store.IndexedBatch``, local shard.
+        Leaves summed gradients in model.flat_grads and returns the global loss (device scalar)."""
         m = self.model
-        inputs, y = tuple(batch[:-1]), batch[-1]
+        if hasattr(batch, "mention_index"):          # resident feature store: rows are gathered by the front end
+            inputs, y = batch, batch.labels
+        else:
+            inputs, y = tuple(batch[:-1]), batch[-1]
         params = m._param_views()
         scores, ctx = m._engine.forward(inputs, params, training=True, num_candidates_model=m.num_candidates_model)
         self.last_scores = scores
@@ -78,7 +81,7 @@ class Trainer:
     def rank_scores(self, batch: Sequence[torch.Tensor], gather: bool = False) -> torch.Tensor:
         """Ranking inference (upstream test_step under no_grad): scores [B_loc, C]; optionally gathered."""
         m = self.model
-        inputs = tuple(batch[:14])
+        inputs = batch if hasattr(batch, "mention_index") else tuple(batch[:14])
         scores, _ = m._engine.forward(inputs, m._param_views(), training=False,
                                       num_candidates_model=m.num_candidates_model)
         return gather_rows(scores, self.group) if gather else scores

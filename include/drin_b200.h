@@ -51,6 +51,9 @@ typedef struct drin_config {
   int32_t static_edges;     /* 0: gcn_edge_type "dynamic" (learned edge update, model.py:130-134);
                                1: "static" (masked edges pass through, model.py:135-136; w_u / w_v of every
                                layer receive no gradient)                                  */
+  int32_t indexed;          /* 0: the 14 input tensors hold exactly this batch (row b = mention b);
+                               1: they are resident feature TABLES and drin_inputs.mention_index /
+                               entity_index select the rows of this batch (drin/data.py:85-108 on device) */
 } drin_config;
 
 /* The 14 model inputs in the order of drin/model.py:164-180 (= drin/data.py:110-125).  Feature tensors
@@ -71,6 +74,14 @@ typedef struct drin_inputs {
   const float* entity_object_score;    /* [B, C, Oe]                      */
   const float* miet_similarity;        /* [B, C]                          */
   const float* mtei_similarity;        /* [B, C]                          */
+  /* Row selection when cfg->indexed != 0 (otherwise ignored; may be NULL).  What MELData.__getitem__ does on the
+   * host (drin/data.py:85-108), done by the front-end kernel instead: the tensors above are whole-split tables
+   * with a leading row dimension N instead of B.
+   *   mention_index [B]    row m of mention b in every mention-side table and in miet / mtei similarity
+   *   entity_index  [B, C] row of candidate (b, c) in the entity-side tables (WikiMEL: qid2idx lookup of
+   *                        entity-name-raw, data.py:88-93).  NULL = WikiDiverse layout, row m * C + c (data.py:95-98). */
+  const int64_t* mention_index;
+  const int64_t* entity_index;
 } drin_inputs;
 
 /* Parameters in state_dict order (drin/model.py:21-24,111-119,159-162); all fp32.
