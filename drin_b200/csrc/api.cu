@@ -77,6 +77,12 @@ int drin_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   return adam_step((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, skip_mask, n, step, lr, beta1, beta2, eps);
 }
 
+int drin_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* skip_mask,
+                       int64_t n, const int32_t* step_dev, float lr, float beta1, float beta2, float eps, void* stream) {
+  return adam_step_dev((cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, skip_mask, n, step_dev, lr, beta1,
+                       beta2, eps);
+}
+
 long long drin_launch_count(void) { return launch_count(); }
 void drin_profile_enable(int32_t on) { prof::enable(on != 0); }
 int drin_profile_collect(double* ms, double* flops, double* bytes, long long* count) {

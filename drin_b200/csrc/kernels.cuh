@@ -128,4 +128,7 @@ int topk_hits(cudaStream_t stream, const float* scores, const unsigned char* lab
 int adam_step(cudaStream_t stream, float* p, const float* g, float* m, float* v, const unsigned char* skip, long long n,
               int step, float lr, float b1, float b2, float eps);
 
+int adam_step_dev(cudaStream_t stream, float* p, const float* g, float* m, float* v, const unsigned char* skip,
+                  long long n, const int* step_dev, float lr, float b1, float b2, float eps);
+
 }  // namespace drin

@@ -13,8 +13,9 @@ class FusedAdam:
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         self.model = model
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
-        self.step_count = 0
         flat = model.flat_params
+        # the step count lives on the device so that a captured CUDA graph of the train step can be replayed
+        self._step = torch.zeros(1, dtype=torch.int32, device=flat.device)
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.skip = model.dead_mask()      # parameters whose grad is None upstream are never stepped
@@ -24,19 +25,23 @@ class FusedAdam:
         flat, grad = m.flat_params, m.flat_grads
         if self.exp_avg.device != flat.device:
             raise RuntimeError("model moved after the optimizer was built")
-        self.step_count += 1
         p = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(flat.device):
-            _lib.check(_lib.load().drin_adam_step(
+            self._step.add_(1)
+            _lib.check(_lib.load().drin_adam_step_dev(
                 p(flat), p(grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.skip), C.c_int64(flat.numel()),
-                C.c_int32(self.step_count), C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]),
-                C.c_float(self.eps), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "drin_adam_step")
+                p(self._step), C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]),
+                C.c_float(self.eps), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "drin_adam_step_dev")
+
+    @property
+    def step_count(self) -> int:
+        return int(self._step)
 
     def state_dict(self):
         return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, lr=self.lr,
                     betas=self.betas, eps=self.eps)
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
+        self._step.fill_(int(sd["step"]))
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -87,6 +87,58 @@ class Trainer:
         return gather_rows(scores, self.group) if gather else scores
 
 
+class GraphedStoreStep:
+    """One CUDA graph for the whole train step (front end .. Adam) over a resident ``FeatureStore``.
+
+    The reference's default batch is 64 mentions (common/args.py:118,126): at that size the ~60 kernels of a step are
+    a few microseconds each and launch / Python overhead dominates.  The step is captured once for a fixed batch size;
+    ``step(idx)`` copies the ``[B]`` mention indices into the graph's static index buffer and replays it.  Single
+    process only (the data-parallel step keeps the eager path: its collectives run between the captured pieces).
+    """
+
+    def __init__(self, trainer: "Trainer", store, batch_size: int, warmup: int = 2):
+        if trainer.world != 1:
+            raise RuntimeError("GraphedStoreStep supports a single process; use Trainer.step for data parallelism")
+        self.trainer, self.store, self.B = trainer, store, int(batch_size)
+        dev = store.device
+        self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self._host_idx = torch.zeros(self.B, dtype=torch.int64).pin_memory()
+        # optimizer / parameter state is advanced by warm-up and capture runs: snapshot and restore it
+        opt, m = trainer.opt, trainer.model
+        saved = (m.flat_params.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt._step.clone())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # allocates the workspace / scratch outside the capture
+                trainer.step(store.select(self.idx))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+            self.loss = trainer.step(store.select(self.idx))
+            self.scores = trainer.last_scores
+        with torch.no_grad():
+            m.flat_params.copy_(saved[0])
+            opt.exp_avg.copy_(saved[1])
+            opt.exp_avg_sq.copy_(saved[2])
+            opt._step.copy_(saved[3])
+
+    def step(self, idx) -> torch.Tensor:
+        """idx: [B] mention indices (host tensor / list, or device tensor).  Returns the loss (static device scalar)."""
+        idx = torch.as_tensor(idx, dtype=torch.int64)
+        if idx.numel() != self.B:
+            raise ValueError(f"graph was captured for {self.B} mentions, got {idx.numel()}")
+        if idx.is_cuda:
+            self.idx.copy_(idx, non_blocking=True)
+        else:
+            if int(idx.min()) < 0 or int(idx.max()) >= len(self.store):
+                raise IndexError("mention index out of range")
+            self._host_idx.copy_(idx)
+            self.idx.copy_(self._host_idx, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
 class HostFeeder:
     """Host -> device path for the loader's CPU batches (what Lightning's ``batch.to(device)`` does before
     reference train.py:46), double buffered on a side stream and copying only the bytes the path reads:

@@ -141,6 +141,11 @@ int drin_topk_hits(const float* scores, const uint8_t* labels, int32_t batch, in
 int drin_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* skip_mask,
                    int64_t n, int32_t step, float lr, float beta1, float beta2, float eps, void* stream);
 
+/* Same update with the 1-based step count read from DEVICE memory (int32), so the whole train step can be captured
+ * in a CUDA graph and replayed: the caller increments *step_dev on the stream before each call. */
+int drin_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* skip_mask,
+                       int64_t n, const int32_t* step_dev, float lr, float beta1, float beta2, float eps, void* stream);
+
 /* ---- stage-level entry points (unit parity tests, ncu) ------------------------------------------- */
 
 /* fp32 -> split-bf16 planes (x ~= hi + lo); lo may be NULL (plain bf16 rounding). n % 4 == 0. */

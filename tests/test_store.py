@@ -157,3 +157,29 @@ def test_indexed_training_matches_oracle():
     assert float((tr.last_scores.cpu() - s_ref).abs().max() / s_ref.abs().max()) < 1e-4
     for k, g in model._grad_views().items():
         assert float((g.cpu() - g_ref[k]).abs().max() / g_ref[k].abs().max()) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_graphed_step_replays_bit_identically_to_eager_steps():
+    """The captured CUDA graph of the whole step (front end .. Adam, device-side step count) gives the same bits as
+    eager steps over the same index batches."""
+    tables, C = make_tables("wikidiverse")
+    store = FeatureStore("wikidiverse", tables, C, device="cuda")
+    batches = [[0, 3, 5, 8], [1, 2, 6, 7], [4, 4, 0, 2]]
+    outs = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = drin_b200.Model(num_candidates_model=C).cuda()
+        tr = drin_b200.Trainer(model, lr=1e-3)
+        losses = []
+        if graphed:
+            gs = drin_b200.GraphedStoreStep(tr, store, 4)
+            for b in batches:
+                losses.append(float(gs.step(b)))
+            assert tr.opt.step_count == 3
+        else:
+            for b in batches:
+                losses.append(float(tr.step(store.select(b))))
+        outs.append((losses, model.flat_params.clone()))
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1])
