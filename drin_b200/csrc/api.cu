@@ -113,6 +113,16 @@ int drin_frontend(const drin_config* cfg, const drin_inputs* in, float* span, fl
   return frontend((cudaStream_t)stream, fa, c.precision == DRIN_BF16);
 }
 
+// Test hook: force a kernel variant that is normally chosen from the problem size (-1 = automatic).
+int drin_debug_option(const char* name, int32_t value) {
+  if (!name) return fail(DRIN_ERR_ARG, "drin_debug_option: null name");
+  if (!strcmp(name, "score_bwd_variant")) debug_set_score_bwd_variant(value);
+  else if (!strcmp(name, "score_fwd_variant")) debug_set_score_fwd_variant(value);
+  else if (!strcmp(name, "layer_fwd_variant")) debug_set_layer_fwd_variant(value);
+  else return fail(DRIN_ERR_ARG, "drin_debug_option: unknown option '%s'", name);
+  return DRIN_OK;
+}
+
 // Test hook: device pointer and shape of a named intermediate inside a planned workspace.
 int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name, int32_t layer, void** ptr,
                       int64_t* rows, int64_t* cols) {

@@ -146,10 +146,181 @@ __global__ void __launch_bounds__(NW * 32) score_bwd_kernel(const ScoreBwdArgs a
   flush_partials<D, NW>(s_part, 3, a.partials, tid);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// score_bwd, warp-autonomous version (default when the batch has enough mentions to fill the machine)
+// ---------------------------------------------------------------------------------------------
+// One warp owns one mention at a time: its mention row, then its C candidate rows in order.  Everything that is
+// summed over rows lives in REGISTERS of that warp -- the mention's dL/da_m over its candidates, and the kernel-long
+// partial column sums (dgamma, dbeta, db_h) -- so the row loop has no CTA barrier, no shared-memory read-modify-write
+// and no atomics; the next candidate row is prefetched into registers while the current one is processed.  Partial
+// sums are combined once at the end of the kernel in a fixed order (bit-reproducible).
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreBwdArgs a, int partial_rows) {
+  constexpr int NV = RowT<D>::NV, NE = NV * 4;
+  extern __shared__ __align__(16) float sm[];
+  float* s_gamma = sm;
+  float* s_beta = s_gamma + D;
+  float* s_am = s_beta + D;                // [NW][D] activated mention row of each warp's current mention
+  float* s_red = s_am + NW * D;            // [NW][3][D] end-of-kernel partials; during the row loop the first two
+                                           // vectors of a warp's slice park xhat / gelu' of its mention row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += NW * 32) {
+    s_gamma[i] = a.gamma[i];
+    s_beta[i] = a.beta[i];
+  }
+  __syncthreads();
+  float* am = s_am + warp * D;
+  float* park = s_red + warp * 3 * D;
+  const long long B = a.B;
+  float pg[NE], pb[NE], ph[NE];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) pg[i] = pb[i] = ph[i] = 0.f;
+
+  // dL/dh of one row from dL/da (in d), given xhat / dact / rstd; accumulates the column partials in registers
+  auto ln_bwd = [&](const RowT<D>& xhat, const RowT<D>& dact, float rstd, RowT<D>& d) {
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 g = *reinterpret_cast<const float4*>(s_gamma + (j * 32 + lane) * 4);
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = 4 * j + k;
+        const float dy = d.v[i] * dact.v[i];
+        pg[i] = fmaf(dy, xhat.v[i], pg[i]);
+        pb[i] += dy;
+        const float dxh = dy * gg[k];
+        d.v[i] = dxh;
+        m1 += dxh;
+        m2 = fmaf(dxh, xhat.v[i], m2);
+      }
+    }
+    m1 = warp_sum(m1) * (1.0f / D);
+    m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      d.v[i] = rstd * (d.v[i] - m1 - xhat.v[i] * m2);
+      ph[i] += d.v[i];
+    }
+  };
+
+  const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
+  for (long long b = gwarp; b < B; b += nwarps) {
+    // ---- mention row: activated vertex -> smem (read back as float4 by the candidate rows), norm
+    RowT<D> xm, actm, dactm;
+    row_load<D>(xm, a.h_mt + b * D, lane);
+    RowT<D> hn;                                           // prefetched candidate row
+    row_load<D>(hn, a.h_et + b * a.C * D, lane);
+    float ds_n = a.dscores[b * a.C];
+    const float rstd_m = row_ln_gelu_recompute<D>(xm, actm, dactm, s_gamma, s_beta, lane);   // xm := xhat
+    float qm = 0.f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) qm = fmaf(actm.v[i], actm.v[i], qm);
+    qm = warp_sum(qm);
+    const float nm = fmaxf(sqrtf(qm), 1e-8f);
+    row_store<D>(actm, am, lane);
+    row_store<D>(xm, park, lane);                          // keep the mention row out of registers during the loop
+    row_store<D>(dactm, park + D, lane);
+    __syncwarp();
+    RowT<D> dam;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) dam.v[i] = 0.f;
+    float coef = 0.f;
+    for (int c = 0; c < a.C; ++c) {
+      const long long r = b * a.C + c;
+      RowT<D> h = hn, e, de;
+      const float ds = ds_n;
+      if (c + 1 < a.C) {
+        row_load<D>(hn, a.h_et + (r + 1) * D, lane);
+        ds_n = a.dscores[r + 1];
+      }
+      const float rstd = row_ln_gelu_recompute<D>(h, e, de, s_gamma, s_beta, lane);          // h := xhat, e := activated
+      float q = 0.f, dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 mv = *reinterpret_cast<const float4*>(am + (j * 32 + lane) * 4);
+        q = fmaf(e.v[4 * j], e.v[4 * j], q); q = fmaf(e.v[4 * j + 1], e.v[4 * j + 1], q);
+        q = fmaf(e.v[4 * j + 2], e.v[4 * j + 2], q); q = fmaf(e.v[4 * j + 3], e.v[4 * j + 3], q);
+        dot = fmaf(e.v[4 * j], mv.x, dot); dot = fmaf(e.v[4 * j + 1], mv.y, dot);
+        dot = fmaf(e.v[4 * j + 2], mv.z, dot); dot = fmaf(e.v[4 * j + 3], mv.w, dot);
+      }
+      q = warp_sum(q);
+      dot = warp_sum(dot);
+      const float ne = fmaxf(sqrtf(q), 1e-8f);
+      const float cs = dot / (nm * ne);
+      const float w1 = ds / (nm * ne), w2 = ds * cs / (ne * ne);
+      coef += ds * cs / (nm * nm);
+      // dL/da_e = w1 * a_m - w2 * a_e ; dL/da_m += w1 * a_e
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 mv = *reinterpret_cast<const float4*>(am + (j * 32 + lane) * 4);
+        const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * j + k;
+          dam.v[i] = fmaf(w1, e.v[i], dam.v[i]);
+          e.v[i] = w1 * mm[k] - w2 * e.v[i];
+        }
+      }
+      ln_bwd(h, de, rstd, e);
+      const long long zr = B + r;
+      row_store_planes<D>(e, a.dh_hi + zr * D, a.dh_lo ? a.dh_lo + zr * D : nullptr, lane);
+    }
+    // ---- mention row gradient: dL/da_m = sum_c w1_c a_e_c - (sum_c ds_c cs_c / nm^2) a_m
+    {
+      RowT<D> t;
+      row_load<D>(t, am, lane);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) dam.v[i] = fmaf(-coef, t.v[i], dam.v[i]);
+    }
+    {
+      RowT<D> xh, da;
+      row_load<D>(xh, park, lane);
+      row_load<D>(da, park + D, lane);
+      ln_bwd(xh, da, rstd_m, dam);
+    }
+    row_store_planes<D>(dam, a.dh_hi + b * D, a.dh_lo ? a.dh_lo + b * D : nullptr, lane);
+    __syncwarp();                                          // am is rewritten by the next mention
+  }
+
+  // ---- fixed-order combination of the per-warp partials; unused rows of the partial buffer are zeroed
+  __syncwarp();
+  float* mine = s_red + warp * 3 * D;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(mine + off) = make_float4(pg[4 * j], pg[4 * j + 1], pg[4 * j + 2], pg[4 * j + 3]);
+    *reinterpret_cast<float4*>(mine + D + off) = make_float4(pb[4 * j], pb[4 * j + 1], pb[4 * j + 2], pb[4 * j + 3]);
+    *reinterpret_cast<float4*>(mine + 2 * D + off) = make_float4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * D; i += NW * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += s_red[w * 3 * D + i];
+    a.partials[(long long)blockIdx.x * 3 * D + i] = t;
+    for (int extra = blockIdx.x + gridDim.x; extra < partial_rows; extra += gridDim.x)
+      a.partials[(long long)extra * 3 * D + i] = 0.f;
+  }
+}
+
+static int g_score_bwd_variant = -1;     // -1 auto, 0 CTA-per-mention kernel, 1 warp-autonomous kernel (test hook)
+void debug_set_score_bwd_variant(int v) { g_score_bwd_variant = v; }
+
 int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a) {
   prof::Scope prof_scope(stream, prof::SCORE);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "score_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
+  constexpr int WNW = 8, WGRID = 148;
+  const bool warp_kernel = g_score_bwd_variant < 0 ? a.B >= WGRID * WNW : g_score_bwd_variant >= 1;
+  if (warp_kernel) {            // enough mentions for one per warp: barrier-free register-accumulating kernel
+    const size_t smem = (size_t)(2 + WNW + 3 * WNW) * D * sizeof(float);
+    DRIN_CUDA(cudaFuncSetAttribute(score_bwd_warp_kernel<D, WNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_bwd_warp_kernel<D, WNW><<<WGRID, WNW * 32, smem, stream>>>(a, BW_CTAS);
+    DRIN_LAUNCH_CHECK();
+    return DRIN_OK;
+  }
   const size_t smem = (size_t)(3 + BW_NW + 3 * BW_NW) * D * sizeof(float);
   DRIN_CUDA(cudaFuncSetAttribute(score_bwd_kernel<D, BW_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_bwd_kernel<D, BW_NW><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);

@@ -244,6 +244,124 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gcn_layer_fwd_kernel(const L
   }
 }
 
+// Warp-autonomous version (default when there is at least one mention per warp).  A warp owns a mention: its four
+// mention-side vectors sit in a private shared-memory slice, the messages to the two mention vertices are summed over
+// the candidates IN REGISTERS (candidate order -> deterministic), and the next candidate's two rows are prefetched
+// into registers while the current candidate is processed.  No CTA barrier and no cross-warp reduction in the loop.
+template <int D, int NW, bool FULL>
+__global__ void __launch_bounds__(NW * 32, 1) gcn_layer_fwd_warp_kernel(const LayerFwdArgs a) {
+  constexpr int NV = RowT<D>::NV, NE = NV * 4;
+  extern __shared__ __align__(16) float sm[];
+  float* s_gamma = sm;
+  float* s_beta = s_gamma + D;
+  float* s_vec = s_beta + D;                                  // [NW][4][D]: mt, mi, g_mt, g_mi of the warp's mention
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long B = a.B, BC = (long long)a.B * a.C;
+  const bool ln = a.ln_gamma != nullptr;
+  const bool dyn = FULL && a.g != nullptr;
+  if (ln) {
+    for (int i = tid; i < D; i += NW * 32) {
+      s_gamma[i] = a.ln_gamma[i];
+      s_beta[i] = a.ln_beta[i];
+    }
+  }
+  __syncthreads();
+  float* v_mt = s_vec + warp * 4 * D;
+  float* v_mi = v_mt + D;
+  float* v_gmt = v_mi + D;
+  float* v_gmi = v_gmt + D;
+  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+  const float en0 = a.en[0], en1 = a.en[1], en2 = a.en[2], en3 = a.en[3];
+  const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
+
+  for (long long b = gwarp; b < B; b += nwarps) {
+    RowT<D> pet, pei;                                         // prefetched rows of the next candidate
+    row_load<D>(pet, a.x_et + b * a.C * D, lane);
+    row_load<D>(pei, a.x_ei + b * a.C * D, lane);
+    {
+      RowT<D> t;
+      row_load<D>(t, a.xm + b * D, lane);
+      row_store<D>(t, v_mt, lane);
+      row_load<D>(t, a.xm + (B + b) * D, lane);
+      row_store<D>(t, v_mi, lane);
+      if (dyn) {
+        row_load<D>(t, a.g + b * D, lane);
+        row_store<D>(t, v_gmt, lane);
+        row_load<D>(t, a.g + (B + b) * D, lane);
+        row_store<D>(t, v_gmi, lane);
+      }
+    }
+    const float beta_mt = dyn ? a.beta_u[b] : 0.f, beta_mi = dyn ? a.beta_u[B + b] : 0.f;
+    __syncwarp();
+    float acc_mt[NE], acc_mi[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) acc_mt[i] = acc_mi[i] = 0.f;
+    long long r = b * a.C;
+    float n0 = a.edges_in[r], n1 = a.edges_in[BC + r], n2 = a.edges_in[2 * BC + r], n3 = a.edges_in[3 * BC + r];
+    for (int c = 0; c < a.C; ++c, ++r) {
+      RowT<D> xet = pet, xei = pei;
+      // enable mask (model.py:122); edge order tt (mt-et), ti (mt-ei), it (mi-et), ii (mi-ei)
+      const float e0 = n0 * en0, e1 = n1 * en1, e2 = n2 * en2, e3 = n3 * en3;
+      if (c + 1 < a.C) {
+        row_load<D>(pet, a.x_et + (r + 1) * D, lane);
+        row_load<D>(pei, a.x_ei + (r + 1) * D, lane);
+        n0 = a.edges_in[r + 1]; n1 = a.edges_in[BC + r + 1]; n2 = a.edges_in[2 * BC + r + 1]; n3 = a.edges_in[3 * BC + r + 1];
+      }
+      if (ln) {
+        row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
+        row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
+      }
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      if (dyn) {
+        d0 = row_dot<D>(xet, v_gmt, lane); d1 = row_dot<D>(xei, v_gmt, lane);
+        d2 = row_dot<D>(xet, v_gmi, lane); d3 = row_dot<D>(xei, v_gmi, lane);
+      }
+      // messages (model.py:124-128,139-146): mt <- e0 et + e1 ei, mi <- e2 et + e3 ei ;
+      // z_et = et + e0 mt + e2 mi ; z_ei = ei + e1 mt + e3 mi
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 mt4 = *reinterpret_cast<const float4*>(v_mt + (j * 32 + lane) * 4);
+        const float4 mi4 = *reinterpret_cast<const float4*>(v_mi + (j * 32 + lane) * 4);
+        const float mt[4] = {mt4.x, mt4.y, mt4.z, mt4.w}, mi[4] = {mi4.x, mi4.y, mi4.z, mi4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * j + k;
+          acc_mt[i] += e0 * xet.v[i] + e1 * xei.v[i];
+          if (FULL) acc_mi[i] += e2 * xet.v[i] + e3 * xei.v[i];
+          xet.v[i] += e0 * mt[k] + e2 * mi[k];
+          if (FULL) xei.v[i] += e1 * mt[k] + e3 * mi[k];
+        }
+      }
+      const long long zr_et = (FULL ? 2 * B : B) + r, zr_ei = 2 * B + BC + r;
+      row_store_planes<D>(xet, a.z_hi + zr_et * D, a.z_lo ? a.z_lo + zr_et * D : nullptr, lane);
+      if (FULL) row_store_planes<D>(xei, a.z_hi + zr_ei * D, a.z_lo ? a.z_lo + zr_ei * D : nullptr, lane);
+      if (dyn) {
+        // dynamic edge update (model.py:131-134,148-153): e' = sigmoid((v . g_u + fu . b_v) / D + e)
+        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
+        if (lane == 0) {
+          a.edges_out[r] = 1.0f / (1.0f + __expf(-((d0 + beta_mt) * invD + e0)));
+          a.edges_out[BC + r] = 1.0f / (1.0f + __expf(-((d1 + beta_mt) * invD + e1)));
+          a.edges_out[2 * BC + r] = 1.0f / (1.0f + __expf(-((d2 + beta_mi) * invD + e2)));
+          a.edges_out[3 * BC + r] = 1.0f / (1.0f + __expf(-((d3 + beta_mi) * invD + e3)));
+        }
+      }
+    }
+    // mention rows: z_m = x_m + mean over ALL C slots of the messages
+    RowT<D> zm;
+    row_load<D>(zm, v_mt, lane);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) zm.v[i] = zm.v[i] + acc_mt[i] * invC;
+    row_store_planes<D>(zm, a.z_hi + b * D, a.z_lo ? a.z_lo + b * D : nullptr, lane);
+    if (FULL) {
+      row_load<D>(zm, v_mi, lane);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) zm.v[i] = zm.v[i] + acc_mi[i] * invC;
+      row_store_planes<D>(zm, a.z_hi + (B + b) * D, a.z_lo ? a.z_lo + (B + b) * D : nullptr, lane);
+    }
+    __syncwarp();                                             // the vector slice is rewritten for the next mention
+  }
+}
+
 template <int D, int NW>
 static int launch_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
   const int nvec = a.full ? 4 : 2;
@@ -262,9 +380,31 @@ static int launch_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
   return DRIN_OK;
 }
 
+template <int D, int NW>
+static int launch_layer_fwd_warp(cudaStream_t stream, const LayerFwdArgs& a) {
+  const size_t smem = (size_t)(2 * D + NW * 4 * D) * sizeof(float);
+  if (a.full) {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_fwd_warp_kernel<D, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    gcn_layer_fwd_warp_kernel<D, NW, true><<<148, NW * 32, smem, stream>>>(a);
+  } else {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_fwd_warp_kernel<D, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    gcn_layer_fwd_warp_kernel<D, NW, false><<<148, NW * 32, smem, stream>>>(a);
+  }
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
+static int g_layer_fwd_variant = -1;     // -1 auto, 0 staged CTA-per-mention, 1 warp-per-mention x 8, 2 x 12 (test hook)
+void debug_set_layer_fwd_variant(int v) { g_layer_fwd_variant = v; }
+
 int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: gcn_embed_dim %d not built (768 only)", a.D);
+  const int variant = g_layer_fwd_variant < 0 ? (a.B >= 148 * 8 ? 1 : 0) : g_layer_fwd_variant;
+  if (variant == 1) return launch_layer_fwd_warp<768, 8>(stream, a);
+  if (variant == 2) return launch_layer_fwd_warp<768, 12>(stream, a);
   return launch_layer_fwd<768, 8>(stream, a);
 }
 
@@ -379,10 +519,65 @@ __global__ void __launch_bounds__(NW * 32) score_kernel(const float* __restrict_
   }
 }
 
+// Warp-autonomous version (default when there is at least one mention per warp): a warp keeps the activated mention
+// row in registers and walks its C candidate rows, prefetching the next row while it normalises the current one --
+// no CTA barrier, one coalesced 3 KB row read per candidate.
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32) score_warp_kernel(const float* __restrict__ h_mt, const float* __restrict__ h_et,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int B, int C,
+                                                              float* __restrict__ scores) {
+  constexpr int NE = RowT<D>::NV * 4;
+  __shared__ __align__(16) float s_gamma[D];
+  __shared__ __align__(16) float s_beta[D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += NW * 32) {
+    s_gamma[i] = gamma[i];
+    s_beta[i] = beta[i];
+  }
+  __syncthreads();
+  const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
+  for (long long b = gwarp; b < B; b += nwarps) {
+    RowT<D> m, hn;
+    row_load<D>(m, h_mt + b * D, lane);
+    row_load<D>(hn, h_et + b * C * D, lane);
+    row_ln_gelu<D>(m, s_gamma, s_beta, lane);
+    float qm = 0.f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) qm = fmaf(m.v[i], m.v[i], qm);
+    const float nm = fmaxf(sqrtf(warp_sum(qm)), 1e-8f);
+    for (int c = 0; c < C; ++c) {
+      const long long r = b * C + c;
+      RowT<D> e = hn;
+      if (c + 1 < C) row_load<D>(hn, h_et + (r + 1) * D, lane);
+      row_ln_gelu<D>(e, s_gamma, s_beta, lane);
+      float q = 0.f, d = 0.f;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        q = fmaf(e.v[i], e.v[i], q);
+        d = fmaf(e.v[i], m.v[i], d);
+      }
+      q = warp_sum(q);
+      d = warp_sum(d);
+      if (lane == 0) scores[r] = d / (nm * fmaxf(sqrtf(q), 1e-8f));
+    }
+  }
+}
+
+static int g_score_fwd_variant = -1;     // -1 auto, 0 CTA-per-mention, 1 warp-per-mention (test hook)
+void debug_set_score_fwd_variant(int v) { g_score_fwd_variant = v; }
+
 int score_fwd(cudaStream_t stream, int D, const float* h_mt, const float* h_et, const float* gamma, const float* beta,
               int B, int C, float* scores) {
   prof::Scope prof_scope(stream, prof::SCORE);
   if (D != 768) return fail(DRIN_ERR_ARG, "score: gcn_embed_dim %d not built (768 only)", D);
+  constexpr int WNW = 8, WGRID = 148;
+  const bool warp_kernel = g_score_fwd_variant < 0 ? B >= WGRID * WNW : g_score_fwd_variant >= 1;
+  if (warp_kernel) {
+    score_warp_kernel<768, WNW><<<WGRID, WNW * 32, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);
+    DRIN_LAUNCH_CHECK();
+    return DRIN_OK;
+  }
   const int grid = B < 148 * 8 ? B : 148 * 8;
   if (C < 32) score_kernel<768, 4><<<grid, 128, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);
   else score_kernel<768, 8><<<grid, 256, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);

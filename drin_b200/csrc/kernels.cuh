@@ -80,6 +80,9 @@ struct ScoreBwdArgs {
   float* partials;         // [ctas][3][D]: dgamma, dbeta, db_h
 };
 int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a);
+void debug_set_score_bwd_variant(int v);
+void debug_set_score_fwd_variant(int v);
+void debug_set_layer_fwd_variant(int v);
 
 struct LayerBwdArgs {
   int B, C, D;

@@ -180,6 +180,10 @@ int drin_profile_collect(double* ms, double* flops, double* bytes, long long* co
 int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name, int32_t layer, void** ptr,
                       int64_t* rows, int64_t* cols);
 
+/* Test hook: force a kernel variant that is normally chosen from the problem size (value -1 = automatic).
+ * Options: "score_bwd_variant" (0 CTA-per-mention kernel, 1 warp-per-mention kernel).  Not part of the drop-in surface. */
+int drin_debug_option(const char* name, int32_t value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,28 @@ CASES = golden_model_cases()
 TOL = 1e-4
 
 
+def _option(name, value):
+    import ctypes as C
+
+    from drin_b200 import _lib
+    _lib.check(_lib.load().drin_debug_option(name.encode(), C.c_int32(value)), "drin_debug_option")
+
+
+@pytest.fixture
+def kernel_variants(request):
+    """Force the kernel variants that are normally picked only at full-size batches (warp-autonomous row kernels),
+    so the golden cases exercise them too; reset to automatic afterwards."""
+    forced = request.param
+    for name in VARIANT_OPTIONS:
+        _option(name, forced)
+    yield forced
+    for name in VARIANT_OPTIONS:
+        _option(name, -1)
+
+
+VARIANT_OPTIONS = ("score_bwd_variant", "score_fwd_variant", "layer_fwd_variant")
+
+
 def _cuda_model(cfg, sd):
     m = drin_b200.Model(num_gcn_layers=cfg.num_gcn_layers, gcn_edge_enabled=cfg.gcn_edge_enabled,
                         gcn_edge_type=cfg.gcn_edge_type, num_candidates_model=cfg.num_candidates_model)
@@ -24,8 +46,9 @@ def _cuda_model(cfg, sd):
     return m.cuda()
 
 
+@pytest.mark.parametrize("kernel_variants", [-1, 1, 2], ids=["auto", "warp-kernels", "warp-kernels-12"], indirect=True)
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-3] for p in CASES])
-def test_train_step_matches_reference_golden_and_oracle(path):
+def test_train_step_matches_reference_golden_and_oracle(path, kernel_variants):
     cfg, batch, sd, fx = load_case(path)
     model = _cuda_model(cfg, sd)
     dbatch = [t.cuda() for t in batch]
