@@ -77,16 +77,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
 // erf-based GELU (F.gelu default) and its derivative from ONE exp + ONE reciprocal:
 // erf(u) = 1 - (a1 t + .. + a5 t^5) exp(-u^2), t = 1 / (1 + p u)  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7),
 // and exp(-u^2) = exp(-x^2 / 2) is also the Gaussian density needed by the derivative.
+// MUFU approximations with flush-to-zero: no denormal pre/post-scaling code around the special-function unit
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float exp2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
   const float u = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
-  const float ex = __expf(-u * u);
+  const float t = rcp_ftz(fmaf(0.3275911f, u, 1.0f));                  // argument >= 1
+  const float ex = exp2_ftz((x * x) * -0.72134752044448170f);          // exp(-x^2 / 2) = exp(-u^2)
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
   poly = fmaf(t, poly, 0.254829592f);
   const float erf_abs = fmaf(-poly * t, ex, 1.0f);
-  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
   g = x * cdf;
   dg = fmaf(x * 0.3989422804014327f, ex, cdf);
 }

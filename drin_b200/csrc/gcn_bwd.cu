@@ -651,10 +651,324 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// gcn_layer_bwd, warp-autonomous version (default when there is at least one mention per warp)
+// ---------------------------------------------------------------------------------------------
+// One warp owns one mention at a time and walks its 2C candidate rows (et_0, ei_0, et_1, ...), prefetching the next
+// row pair (vertex row + its dz row) into registers.  The mention-side vectors and the per-mention sums over
+// candidates (messages to the mention vertices, g gradients) live in a private shared-memory slice of the warp; the
+// kernel-long column sums (bias / LayerNorm parameter gradients) live in registers.  No CTA barrier in the row loop;
+// all sums run in candidate order and the per-warp partials are combined once, in a fixed order, at the end.
+template <int D, int NW, bool FULL>
+__global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const LayerBwdArgs a, int partial_rows) {
+  constexpr int NV = RowT<D>::NV, NE = NV * 4;
+  constexpr int NVEC = FULL ? 6 : 3;             // xm_t, xm_i, dz_mt (, dz_mi, g_mt, g_mi)
+  constexpr int NACC = FULL ? 4 : 2;             // A_mt, A_mi (, G_mt, G_mi)
+  constexpr int SLICE = (NVEC + NACC) * D;
+  extern __shared__ __align__(16) float sm[];
+  float* s_gamma = sm;
+  float* s_beta = s_gamma + D;
+  float* s_slices = s_beta + D;                  // [NW][SLICE]; reused for the end-of-kernel partials ([NW][3][D])
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long B = a.B, BC = (long long)a.B * a.C;
+  const bool ln = a.ln_gamma != nullptr;
+  const bool dyn = FULL && a.g != nullptr;
+  const bool want_de = a.dedges_in != nullptr;
+  if (ln) {
+    for (int i = tid; i < D; i += NW * 32) {
+      s_gamma[i] = a.ln_gamma[i];
+      s_beta[i] = a.ln_beta[i];
+    }
+  }
+  __syncthreads();
+  float* v_xmt = s_slices + warp * SLICE;
+  float* v_xmi = v_xmt + D;
+  float* v_dzmt = v_xmi + D;
+  float* v_dzmi = v_dzmt + D;                    // FULL only (pointer arithmetic below stays inside the slice)
+  float* v_gmt = v_dzmi + D;
+  float* v_gmi = v_gmt + D;
+  float* A_mt = v_xmt + NVEC * D;
+  float* A_mi = A_mt + D;
+  float* G_mt = A_mi + D;                        // FULL only
+  float* G_mi = G_mt + D;
+  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+  const float* dz_mt = a.dz;
+  const float* dz_mi = FULL ? a.dz + B * D : nullptr;
+  const float* dz_et = a.dz + (FULL ? 2 * B : B) * D;
+  const float* dz_ei = FULL ? a.dz + (2 * B + BC) * D : nullptr;
+  float p0[NE], p1[NE], p2[NE];                  // ln: dgamma, dbeta, db_h ; else: db_et, db_ei, (unused)
+#pragma unroll
+  for (int i = 0; i < NE; ++i) p0[i] = p1[i] = p2[i] = 0.f;
+
+  const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
+  for (long long b = gwarp; b < B; b += nwarps) {
+    const long long r0 = b * a.C;
+    RowT<D> px, pd;                              // prefetched vertex row and dz row of the next step
+    row_load<D>(px, a.x_et + r0 * D, lane);
+    row_load<D>(pd, dz_et + r0 * D, lane);
+    {
+      RowT<D> t;
+      row_load<D>(t, a.xm + b * D, lane); row_store<D>(t, v_xmt, lane);
+      row_load<D>(t, a.xm + (B + b) * D, lane); row_store<D>(t, v_xmi, lane);
+      row_load<D>(t, dz_mt + b * D, lane); row_store<D>(t, v_dzmt, lane);
+      if (FULL) { row_load<D>(t, dz_mi + b * D, lane); row_store<D>(t, v_dzmi, lane); }
+      if (dyn) {
+        row_load<D>(t, a.g + b * D, lane); row_store<D>(t, v_gmt, lane);
+        row_load<D>(t, a.g + (B + b) * D, lane); row_store<D>(t, v_gmi, lane);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(A_mt + (j * 32 + lane) * 4) = z;
+        *reinterpret_cast<float4*>(A_mi + (j * 32 + lane) * 4) = z;
+        if (dyn) {
+          *reinterpret_cast<float4*>(G_mt + (j * 32 + lane) * 4) = z;
+          *reinterpret_cast<float4*>(G_mi + (j * 32 + lane) * 4) = z;
+        }
+      }
+    }
+    __syncwarp();
+    float dbeta_mt = 0.f, dbeta_mi = 0.f;
+    float e[4], ds[4] = {0.f, 0.f, 0.f, 0.f};
+    float ne[4], no[4] = {0.f, 0.f, 0.f, 0.f}, ndo[4] = {0.f, 0.f, 0.f, 0.f};   // scalars of the NEXT candidate
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ne[k] = a.edges_in[k * BC + r0];
+      if (dyn) {
+        no[k] = a.edges_out[k * BC + r0];
+        ndo[k] = a.dedges_out[k * BC + r0];
+      }
+    }
+    for (int step = 0; step < 2 * a.C; ++step) {
+      const int c = step >> 1, kind = step & 1;
+      const long long r = r0 + c;
+      if (kind == 0) {
+        // per-candidate scalars (enable mask model.py:122; sigmoid backward of the dynamic edge update), loaded one
+        // candidate ahead so their latency is off the critical path
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          e[k] = ne[k] * a.en[k];
+          if (dyn) ds[k] = ndo[k] * no[k] * (1.f - no[k]);
+        }
+        if (dyn) {
+          dbeta_mt += (ds[0] + ds[1]) * invD;
+          dbeta_mi += (ds[2] + ds[3]) * invD;
+        }
+        if (c + 1 < a.C) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ne[k] = a.edges_in[k * BC + r + 1];
+            if (dyn) {
+              no[k] = a.edges_out[k * BC + r + 1];
+              ndo[k] = a.dedges_out[k * BC + r + 1];
+            }
+          }
+        }
+      }
+      const bool has_dz = FULL || !kind;
+      RowT<D> x = px, d;
+      if (has_dz) {
+        d = pd;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) d.v[i] = 0.f;
+      }
+      // prefetch the next step's rows: ei of this candidate, or et of the next candidate
+      if (kind == 0) {
+        row_load<D>(px, a.x_ei + r * D, lane);
+        if (FULL) row_load<D>(pd, dz_ei + r * D, lane);
+      } else if (c + 1 < a.C) {
+        row_load<D>(px, a.x_et + (r + 1) * D, lane);
+        row_load<D>(pd, dz_et + (r + 1) * D, lane);
+      }
+      const float e_mt = e[kind ? 1 : 0], e_mi = e[kind ? 3 : 2];
+      const float ds_mt = ds[kind ? 1 : 0], ds_mi = ds[kind ? 3 : 2];
+      RowT<D> xhat, dact;
+      float rstd = 0.f;
+      if (ln) {
+        xhat = x;
+        rstd = row_ln_gelu_recompute<D>(xhat, x, dact, s_gamma, s_beta, lane);     // x := activated row
+      }
+      const float ec_mt = e_mt * invC, ec_mi = e_mi * invC, dd_mt = ds_mt * invD, dd_mi = ds_mi * invD;
+      float pd_mt = 0.f, pd_mi = 0.f, q_mt = 0.f, q_mi = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int off = (j * 32 + lane) * 4;
+        const float4 zmt4 = *reinterpret_cast<const float4*>(v_dzmt + off);
+        const float zmt[4] = {zmt4.x, zmt4.y, zmt4.z, zmt4.w};
+        float zmi[4] = {0.f, 0.f, 0.f, 0.f}, gmt[4] = {0.f, 0.f, 0.f, 0.f}, gmi[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FULL) {
+          const float4 t = *reinterpret_cast<const float4*>(v_dzmi + off);
+          zmi[0] = t.x; zmi[1] = t.y; zmi[2] = t.z; zmi[3] = t.w;
+        }
+        if (dyn) {
+          const float4 t = *reinterpret_cast<const float4*>(v_gmt + off);
+          gmt[0] = t.x; gmt[1] = t.y; gmt[2] = t.z; gmt[3] = t.w;
+          const float4 u = *reinterpret_cast<const float4*>(v_gmi + off);
+          gmi[0] = u.x; gmi[1] = u.y; gmi[2] = u.z; gmi[3] = u.w;
+        }
+        if (want_de) {
+          const float4 xt4 = *reinterpret_cast<const float4*>(v_xmt + off);
+          const float4 xi4 = *reinterpret_cast<const float4*>(v_xmi + off);
+          const float xt[4] = {xt4.x, xt4.y, xt4.z, xt4.w}, xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * j + k;
+            pd_mt = fmaf(x.v[i], zmt[k], pd_mt);
+            if (FULL) pd_mi = fmaf(x.v[i], zmi[k], pd_mi);
+            if (has_dz) {
+              q_mt = fmaf(d.v[i], xt[k], q_mt);
+              q_mi = fmaf(d.v[i], xi[k], q_mi);
+            }
+          }
+        }
+        if (has_dz) {      // messages to the mention vertices: sums of the ORIGINAL dz rows
+          float4 amt = *reinterpret_cast<float4*>(A_mt + off);
+          float4 ami = *reinterpret_cast<float4*>(A_mi + off);
+          amt.x = fmaf(e_mt, d.v[4 * j], amt.x); amt.y = fmaf(e_mt, d.v[4 * j + 1], amt.y);
+          amt.z = fmaf(e_mt, d.v[4 * j + 2], amt.z); amt.w = fmaf(e_mt, d.v[4 * j + 3], amt.w);
+          ami.x = fmaf(e_mi, d.v[4 * j], ami.x); ami.y = fmaf(e_mi, d.v[4 * j + 1], ami.y);
+          ami.z = fmaf(e_mi, d.v[4 * j + 2], ami.z); ami.w = fmaf(e_mi, d.v[4 * j + 3], ami.w);
+          *reinterpret_cast<float4*>(A_mt + off) = amt;
+          *reinterpret_cast<float4*>(A_mi + off) = ami;
+        }
+        if (dyn) {         // gradient of g = fu W_v: sums of the activated vertex rows
+          float4 gt = *reinterpret_cast<float4*>(G_mt + off);
+          float4 gi = *reinterpret_cast<float4*>(G_mi + off);
+          gt.x = fmaf(dd_mt, x.v[4 * j], gt.x); gt.y = fmaf(dd_mt, x.v[4 * j + 1], gt.y);
+          gt.z = fmaf(dd_mt, x.v[4 * j + 2], gt.z); gt.w = fmaf(dd_mt, x.v[4 * j + 3], gt.w);
+          gi.x = fmaf(dd_mi, x.v[4 * j], gi.x); gi.y = fmaf(dd_mi, x.v[4 * j + 1], gi.y);
+          gi.z = fmaf(dd_mi, x.v[4 * j + 2], gi.z); gi.w = fmaf(dd_mi, x.v[4 * j + 3], gi.w);
+          *reinterpret_cast<float4*>(G_mt + off) = gt;
+          *reinterpret_cast<float4*>(G_mi + off) = gi;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * j + k;
+          d.v[i] = fmaf(ec_mt, zmt[k], d.v[i]);
+          if (FULL) d.v[i] = fmaf(ec_mi, zmi[k], d.v[i]);
+          if (dyn) d.v[i] += dd_mt * gmt[k] + dd_mi * gmi[k];
+        }
+      }
+      if (want_de) {
+        pd_mt = warp_sum(pd_mt); q_mt = warp_sum(q_mt); q_mi = warp_sum(q_mi);
+        if (FULL) pd_mi = warp_sum(pd_mi);
+        // edges (mt,row) and (mi,row): tt / it for the et row, ti / ii for the ei row; the mask is applied again
+        if (lane == 0) {
+          const int k_mt = kind ? 1 : 0, k_mi = kind ? 3 : 2;
+          a.dedges_in[k_mt * BC + r] = (pd_mt * invC + q_mt + ds_mt) * a.en[k_mt];
+          a.dedges_in[k_mi * BC + r] = (pd_mi * invC + q_mi + ds_mi) * a.en[k_mi];
+        }
+      }
+      if (ln) {
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const float4 g = *reinterpret_cast<const float4*>(s_gamma + (j * 32 + lane) * 4);
+          const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * j + k;
+            const float dy = d.v[i] * dact.v[i];
+            p0[i] = fmaf(dy, xhat.v[i], p0[i]);
+            p1[i] += dy;
+            const float dxh = dy * gg[k];
+            d.v[i] = dxh;
+            m1 += dxh;
+            m2 = fmaf(dxh, xhat.v[i], m2);
+          }
+        }
+        m1 = warp_sum(m1) * (1.0f / D);
+        m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          d.v[i] = rstd * (d.v[i] - m1 - xhat.v[i] * m2);
+          p2[i] += d.v[i];
+        }
+      } else if (kind == 0) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) p0[i] += d.v[i];          // db_et (bias of the entity-text projection)
+      } else {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) p1[i] += d.v[i];          // db_ei
+      }
+      const long long orow = (kind ? 2 * B + BC : 2 * B) + r;  // row in the [mt; mi; et; ei] layout
+      row_store_planes<D>(d, a.dcand_hi + orow * D, a.dcand_lo ? a.dcand_lo + orow * D : nullptr, lane);
+    }
+    // ---- mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
+    __syncwarp();
+    {
+      RowT<D> t, z;
+      row_load<D>(t, A_mt, lane);
+      row_load<D>(z, v_dzmt, lane);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) t.v[i] += z.v[i];
+      row_store<D>(t, a.dxm + b * D, lane);
+      row_load<D>(t, A_mi, lane);
+      if (FULL) {
+        row_load<D>(z, v_dzmi, lane);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) t.v[i] += z.v[i];
+      }
+      row_store<D>(t, a.dxm + (B + b) * D, lane);
+      if (dyn) {
+        row_load<D>(t, G_mt, lane);
+        row_store_planes<D>(t, a.dg_hi + b * D, a.dg_lo ? a.dg_lo + b * D : nullptr, lane);
+        row_load<D>(t, G_mi, lane);
+        row_store_planes<D>(t, a.dg_hi + (B + b) * D, a.dg_lo ? a.dg_lo + (B + b) * D : nullptr, lane);
+        if (lane == 0) {
+          a.dbeta[b] = dbeta_mt;
+          a.dbeta[B + b] = dbeta_mi;
+        }
+      }
+    }
+    __syncwarp();                                // the slice is rewritten for the next mention
+  }
+
+  // ---- fixed-order combination of the per-warp column partials; unused rows of the partial buffer are zeroed
+  __syncthreads();
+  float* mine = s_slices + warp * 3 * D;         // SLICE >= 5 D >= 3 D
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int off = (j * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(mine + off) = make_float4(p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+    *reinterpret_cast<float4*>(mine + D + off) = make_float4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+    *reinterpret_cast<float4*>(mine + 2 * D + off) = make_float4(p2[4 * j], p2[4 * j + 1], p2[4 * j + 2], p2[4 * j + 3]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * D; i += NW * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += s_slices[w * 3 * D + i];
+    a.partials[(long long)blockIdx.x * 3 * D + i] = t;
+    for (int extra = blockIdx.x + gridDim.x; extra < partial_rows; extra += gridDim.x)
+      a.partials[(long long)extra * 3 * D + i] = 0.f;
+  }
+}
+
+static int g_layer_bwd_variant = -1;     // -1 auto, 0 staged CTA-per-SM kernel, 1 warp-per-mention kernel (test hook)
+void debug_set_layer_bwd_variant(int v) { g_layer_bwd_variant = v; }
+
+template <int D, int NW, bool FULL>
+static int launch_layer_bwd_warp(cudaStream_t stream, const LayerBwdArgs& a) {
+  const size_t smem = (size_t)(2 + NW * (FULL ? 10 : 5)) * D * sizeof(float);
+  DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_warp_kernel<D, NW, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gcn_layer_bwd_warp_kernel<D, NW, FULL><<<BS_GRID, NW * 32, smem, stream>>>(a, BS_GRID);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
+  const bool warp_kernel = g_layer_bwd_variant < 0 ? a.B >= BS_GRID * 7 : g_layer_bwd_variant >= 1;
+  if (warp_kernel) {
+    // 7 warps x 30 KB (full layers) or 8 warps x 15 KB (last layer) of private shared memory per SM
+    return a.full ? launch_layer_bwd_warp<D, 7, true>(stream, a) : launch_layer_bwd_warp<D, 8, false>(stream, a);
+  }
+
   // persistent: every CTA of the fixed partial-sum grid writes its partials
   const size_t smem = (size_t)(BS_STAGES * (4 * BS_CH + 6) * D + 2 * D + 2 * BS_CH * 8 + 2 * BS_CH * 8) * sizeof(float);
   if (a.full) {

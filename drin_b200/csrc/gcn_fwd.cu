@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(NW * 32) score_kernel(const float* __restrict_
 // row in registers and walks its C candidate rows, prefetching the next row while it normalises the current one --
 // no CTA barrier, one coalesced 3 KB row read per candidate.
 template <int D, int NW>
-__global__ void __launch_bounds__(NW * 32) score_warp_kernel(const float* __restrict__ h_mt, const float* __restrict__ h_et,
+__global__ void __launch_bounds__(NW * 32, 2) score_warp_kernel(const float* __restrict__ h_mt, const float* __restrict__ h_et,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int B, int C,
                                                               float* __restrict__ scores) {
@@ -571,7 +571,7 @@ int score_fwd(cudaStream_t stream, int D, const float* h_mt, const float* h_et, 
               int B, int C, float* scores) {
   prof::Scope prof_scope(stream, prof::SCORE);
   if (D != 768) return fail(DRIN_ERR_ARG, "score: gcn_embed_dim %d not built (768 only)", D);
-  constexpr int WNW = 8, WGRID = 148;
+  constexpr int WNW = 8, WGRID = 148 * 2;     // 2 CTAs / SM (<= 128 registers)
   const bool warp_kernel = g_score_fwd_variant < 0 ? B >= WGRID * WNW : g_score_fwd_variant >= 1;
   if (warp_kernel) {
     score_warp_kernel<768, WNW><<<WGRID, WNW * 32, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);

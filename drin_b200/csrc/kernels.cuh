@@ -83,6 +83,7 @@ int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a);
 void debug_set_score_bwd_variant(int v);
 void debug_set_score_fwd_variant(int v);
 void debug_set_layer_fwd_variant(int v);
+void debug_set_layer_bwd_variant(int v);
 
 struct LayerBwdArgs {
   int B, C, D;

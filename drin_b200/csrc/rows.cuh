@@ -72,14 +72,15 @@ __device__ __forceinline__ void row_ln_gelu(RowT<D>& r, const float* __restrict_
     q += d * d;
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  const float shift = -mean * rstd;                        // xhat = h * rstd + shift: one FFMA per element
 #pragma unroll
   for (int j = 0; j < RowT<D>::NV; ++j) {
     const float4 g = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
     const float4 b = *reinterpret_cast<const float4*>(beta + (j * 32 + lane) * 4);
-    r.v[4 * j] = gelu_f((r.v[4 * j] - mean) * rstd * g.x + b.x);
-    r.v[4 * j + 1] = gelu_f((r.v[4 * j + 1] - mean) * rstd * g.y + b.y);
-    r.v[4 * j + 2] = gelu_f((r.v[4 * j + 2] - mean) * rstd * g.z + b.z);
-    r.v[4 * j + 3] = gelu_f((r.v[4 * j + 3] - mean) * rstd * g.w + b.w);
+    r.v[4 * j] = gelu_f(fmaf(fmaf(r.v[4 * j], rstd, shift), g.x, b.x));
+    r.v[4 * j + 1] = gelu_f(fmaf(fmaf(r.v[4 * j + 1], rstd, shift), g.y, b.y));
+    r.v[4 * j + 2] = gelu_f(fmaf(fmaf(r.v[4 * j + 2], rstd, shift), g.z, b.z));
+    r.v[4 * j + 3] = gelu_f(fmaf(fmaf(r.v[4 * j + 3], rstd, shift), g.w, b.w));
   }
 }
 
@@ -164,6 +165,7 @@ __device__ __forceinline__ float row_ln_gelu_recompute(RowT<D>& h, RowT<D>& act,
     q += t * t;
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  const float shift = -mean * rstd;
 #pragma unroll
   for (int j = 0; j < RowT<D>::NV; ++j) {
     const int off = (j * 32 + lane) * 4;
@@ -172,7 +174,7 @@ __device__ __forceinline__ float row_ln_gelu_recompute(RowT<D>& h, RowT<D>& act,
     const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float xh = (h.v[4 * j + k] - mean) * rstd;
+      const float xh = fmaf(h.v[4 * j + k], rstd, shift);
       h.v[4 * j + k] = xh;
       gelu_both(fmaf(xh, gg[k], bb[k]), act.v[4 * j + k], dact.v[4 * j + k]);
     }

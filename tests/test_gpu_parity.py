@@ -36,7 +36,7 @@ def kernel_variants(request):
         _option(name, -1)
 
 
-VARIANT_OPTIONS = ("score_bwd_variant", "score_fwd_variant", "layer_fwd_variant")
+VARIANT_OPTIONS = ("score_bwd_variant", "score_fwd_variant", "layer_fwd_variant", "layer_bwd_variant")
 
 
 def _cuda_model(cfg, sd):
