@@ -14,6 +14,8 @@
 // bit-reproducible run to run.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "pipe.cuh"
 #include "rows.cuh"
@@ -235,6 +237,11 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
         row_load<D>(hn, a.h_et + (r + 1) * D, lane);
         ds_n = a.dscores[r + 1];
       }
+      if (lane == 0) {        // DRAM latency runs ahead of the register prefetch (bulk L2 prefetch)
+        const long long pr = c + 3 < a.C ? r + 3 : (b + nwarps < B ? (b + nwarps) * a.C + min(c + 3 - a.C, a.C - 1) : -1);
+        if (pr >= 0) l2_prefetch(a.h_et + pr * D, D * 4);
+      }
+      asm volatile("" ::: "memory");                         // keeps the prefetch and the row's math apart (registers)
       const float rstd = row_ln_gelu_recompute<D>(h, e, de, s_gamma, s_beta, lane);          // h := xhat, e := activated
       float q = 0.f, dot = 0.f;
 #pragma unroll
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
       const float cs = dot / (nm * ne);
       const float w1 = ds / (nm * ne), w2 = ds * cs / (ne * ne);
       coef += ds * cs / (nm * nm);
+      asm volatile("" ::: "memory");
       // dL/da_e = w1 * a_m - w2 * a_e ; dL/da_m += w1 * a_e
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
@@ -263,7 +271,9 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
           e.v[i] = w1 * mm[k] - w2 * e.v[i];
         }
       }
+      asm volatile("" ::: "memory");
       ln_bwd(h, de, rstd, e);
+      asm volatile("" ::: "memory");
       const long long zr = B + r;
       row_store_planes<D>(e, a.dh_hi + zr * D, a.dh_lo ? a.dh_lo + zr * D : nullptr, lane);
     }
@@ -660,7 +670,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
 // candidates (messages to the mention vertices, g gradients) live in a private shared-memory slice of the warp; the
 // kernel-long column sums (bias / LayerNorm parameter gradients) live in registers.  No CTA barrier in the row loop;
 // all sums run in candidate order and the per-warp partials are combined once, in a fixed order, at the end.
-template <int D, int NW, bool FULL>
+template <int D, int NW, bool FULL, bool LN>
 __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const LayerBwdArgs a, int partial_rows) {
   constexpr int NV = RowT<D>::NV, NE = NV * 4;
   constexpr int NVEC = FULL ? 6 : 3;             // xm_t, xm_i, dz_mt (, dz_mi, g_mt, g_mi)
@@ -672,7 +682,8 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
   float* s_slices = s_beta + D;                  // [NW][SLICE]; reused for the end-of-kernel partials ([NW][3][D])
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long B = a.B, BC = (long long)a.B * a.C;
-  const bool ln = a.ln_gamma != nullptr;
+  constexpr bool ln = LN;                       // LayerNorm + GELU in front of the candidate rows (layers > 0)
+  constexpr bool LATE_DZ = LN && FULL;           // middle layers (L >= 3): too many live rows to prefetch dz as well
   const bool dyn = FULL && a.g != nullptr;
   const bool want_de = a.dedges_in != nullptr;
   if (ln) {
@@ -702,11 +713,35 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
   for (int i = 0; i < NE; ++i) p0[i] = p1[i] = p2[i] = 0.f;
 
   const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
+  constexpr uint32_t ROW_BYTES = D * sizeof(float);
+  // L2 prefetch of everything one candidate needs (lane 0): runs the DRAM latency two candidates ahead of the
+  // register loads, which then hit L2
+  auto prefetch_candidate = [&](long long r) {
+    l2_prefetch(a.x_et + r * D, ROW_BYTES);
+    l2_prefetch(a.x_ei + r * D, ROW_BYTES);
+    l2_prefetch(dz_et + r * D, ROW_BYTES);
+    if (FULL) l2_prefetch(dz_ei + r * D, ROW_BYTES);
+  };
+  auto prefetch_mention = [&](long long m) {
+    l2_prefetch(a.xm + m * D, ROW_BYTES);
+    l2_prefetch(a.xm + (B + m) * D, ROW_BYTES);
+    l2_prefetch(dz_mt + m * D, ROW_BYTES);
+    if (FULL) l2_prefetch(dz_mi + m * D, ROW_BYTES);
+    if (dyn) {
+      l2_prefetch(a.g + m * D, ROW_BYTES);
+      l2_prefetch(a.g + (B + m) * D, ROW_BYTES);
+    }
+  };
+  if (lane == 0 && gwarp < B) {
+    prefetch_candidate(gwarp * a.C);
+    if (a.C > 1) prefetch_candidate(gwarp * a.C + 1);
+  }
+
   for (long long b = gwarp; b < B; b += nwarps) {
     const long long r0 = b * a.C;
-    RowT<D> px, pd;                              // prefetched vertex row and dz row of the next step
-    row_load<D>(px, a.x_et + r0 * D, lane);
-    row_load<D>(pd, dz_et + r0 * D, lane);
+    RowT<D> ax, ad, bx, bd;                      // register sets of the et row pair and the ei row pair
+    row_load<D>(ax, a.x_et + r0 * D, lane);
+    if (!LATE_DZ) row_load<D>(ad, dz_et + r0 * D, lane);
     {
       RowT<D> t;
       row_load<D>(t, a.xm + b * D, lane); row_store<D>(t, v_xmt, lane);
@@ -740,50 +775,20 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
         ndo[k] = a.dedges_out[k * BC + r0];
       }
     }
-    for (int step = 0; step < 2 * a.C; ++step) {
-      const int c = step >> 1, kind = step & 1;
-      const long long r = r0 + c;
-      if (kind == 0) {
-        // per-candidate scalars (enable mask model.py:122; sigmoid backward of the dynamic edge update), loaded one
-        // candidate ahead so their latency is off the critical path
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          e[k] = ne[k] * a.en[k];
-          if (dyn) ds[k] = ndo[k] * no[k] * (1.f - no[k]);
-        }
-        if (dyn) {
-          dbeta_mt += (ds[0] + ds[1]) * invD;
-          dbeta_mi += (ds[2] + ds[3]) * invD;
-        }
-        if (c + 1 < a.C) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ne[k] = a.edges_in[k * BC + r + 1];
-            if (dyn) {
-              no[k] = a.edges_out[k * BC + r + 1];
-              ndo[k] = a.dedges_out[k * BC + r + 1];
-            }
-          }
-        }
-      }
-      const bool has_dz = FULL || !kind;
-      RowT<D> x = px, d;
-      if (has_dz) {
-        d = pd;
-      } else {
+
+    // one vertex row (kind 0: entity text, 1: entity image) of candidate row r, in place: x -> unused, d -> dL/dx
+    // LATE_DZ: the dz row is loaded here, from L2 (bulk-prefetched two candidates ahead); its latency hides behind
+    // the LayerNorm/GELU recompute and the registers of a second prefetched row are saved.
+    auto process_row = [&](auto kind_c, long long r, RowT<D>& x, RowT<D>& d, const float* dzrow, float e_mt, float e_mi,
+                           float ds_mt, float ds_mi) {
+      constexpr int kind = decltype(kind_c)::value;
+      constexpr bool has_dz = FULL || kind == 0;
+      if (!has_dz) {
 #pragma unroll
         for (int i = 0; i < NE; ++i) d.v[i] = 0.f;
+      } else if (LATE_DZ) {
+        row_load<D>(d, dzrow, lane);
       }
-      // prefetch the next step's rows: ei of this candidate, or et of the next candidate
-      if (kind == 0) {
-        row_load<D>(px, a.x_ei + r * D, lane);
-        if (FULL) row_load<D>(pd, dz_ei + r * D, lane);
-      } else if (c + 1 < a.C) {
-        row_load<D>(px, a.x_et + (r + 1) * D, lane);
-        row_load<D>(pd, dz_et + (r + 1) * D, lane);
-      }
-      const float e_mt = e[kind ? 1 : 0], e_mi = e[kind ? 3 : 2];
-      const float ds_mt = ds[kind ? 1 : 0], ds_mi = ds[kind ? 3 : 2];
       RowT<D> xhat, dact;
       float rstd = 0.f;
       if (ln) {
@@ -856,7 +861,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
         if (FULL) pd_mi = warp_sum(pd_mi);
         // edges (mt,row) and (mi,row): tt / it for the et row, ti / ii for the ei row; the mask is applied again
         if (lane == 0) {
-          const int k_mt = kind ? 1 : 0, k_mi = kind ? 3 : 2;
+          constexpr int k_mt = kind ? 1 : 0, k_mi = kind ? 3 : 2;
           a.dedges_in[k_mt * BC + r] = (pd_mt * invC + q_mt + ds_mt) * a.en[k_mt];
           a.dedges_in[k_mi * BC + r] = (pd_mi * invC + q_mi + ds_mi) * a.en[k_mi];
         }
@@ -895,6 +900,49 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
       }
       const long long orow = (kind ? 2 * B + BC : 2 * B) + r;  // row in the [mt; mi; et; ei] layout
       row_store_planes<D>(d, a.dcand_hi + orow * D, a.dcand_lo ? a.dcand_lo + orow * D : nullptr, lane);
+    };
+
+    for (int c = 0; c < a.C; ++c) {
+      const long long r = r0 + c;
+      // per-candidate scalars (enable mask model.py:122; sigmoid backward of the dynamic edge update), loaded one
+      // candidate ahead so their latency is off the critical path
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k] = ne[k] * a.en[k];
+        if (dyn) ds[k] = ndo[k] * no[k] * (1.f - no[k]);
+      }
+      if (dyn) {
+        dbeta_mt += (ds[0] + ds[1]) * invD;
+        dbeta_mi += (ds[2] + ds[3]) * invD;
+      }
+      if (c + 1 < a.C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ne[k] = a.edges_in[k * BC + r + 1];
+          if (dyn) {
+            no[k] = a.edges_out[k * BC + r + 1];
+            ndo[k] = a.dedges_out[k * BC + r + 1];
+          }
+        }
+      }
+      if (lane == 0) {        // L2 prefetch two candidates ahead (crossing into the warp's next mention)
+        if (c + 2 < a.C) {
+          prefetch_candidate(r + 2);
+        } else if (b + nwarps < B) {
+          const long long nb = b + nwarps;
+          prefetch_candidate(nb * a.C + (c + 2 - a.C < a.C ? c + 2 - a.C : a.C - 1));
+          if (c + 2 == a.C) prefetch_mention(nb);
+        }
+      }
+      row_load<D>(bx, a.x_ei + r * D, lane);                    // ei rows arrive while the et row is processed
+      if (FULL && !LATE_DZ) row_load<D>(bd, dz_ei + r * D, lane);
+      process_row(std::integral_constant<int, 0>{}, r, ax, ad, dz_et + r * D, e[0], e[2], ds[0], ds[2]);
+      asm volatile("" ::: "memory");                            // keep the two rows' instruction streams apart (registers)
+      if (c + 1 < a.C) {                                        // next candidate's et rows arrive during the ei row
+        row_load<D>(ax, a.x_et + (r + 1) * D, lane);
+        if (!LATE_DZ) row_load<D>(ad, dz_et + (r + 1) * D, lane);
+      }
+      process_row(std::integral_constant<int, 1>{}, r, bx, bd, FULL ? dz_ei + r * D : nullptr, e[1], e[3], ds[1], ds[3]);
     }
     // ---- mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
     __syncwarp();
@@ -950,11 +998,11 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
 static int g_layer_bwd_variant = -1;     // -1 auto, 0 staged CTA-per-SM kernel, 1 warp-per-mention kernel (test hook)
 void debug_set_layer_bwd_variant(int v) { g_layer_bwd_variant = v; }
 
-template <int D, int NW, bool FULL>
+template <int D, int NW, bool FULL, bool LN>
 static int launch_layer_bwd_warp(cudaStream_t stream, const LayerBwdArgs& a) {
   const size_t smem = (size_t)(2 + NW * (FULL ? 10 : 5)) * D * sizeof(float);
-  DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_warp_kernel<D, NW, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gcn_layer_bwd_warp_kernel<D, NW, FULL><<<BS_GRID, NW * 32, smem, stream>>>(a, BS_GRID);
+  DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_warp_kernel<D, NW, FULL, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gcn_layer_bwd_warp_kernel<D, NW, FULL, LN><<<BS_GRID, NW * 32, smem, stream>>>(a, BS_GRID);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }
@@ -966,7 +1014,9 @@ int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
   const bool warp_kernel = g_layer_bwd_variant < 0 ? a.B >= BS_GRID * 7 : g_layer_bwd_variant >= 1;
   if (warp_kernel) {
     // 7 warps x 30 KB (full layers) or 8 warps x 15 KB (last layer) of private shared memory per SM
-    return a.full ? launch_layer_bwd_warp<D, 7, true>(stream, a) : launch_layer_bwd_warp<D, 8, false>(stream, a);
+    const bool ln = a.ln_gamma != nullptr;
+    if (a.full) return ln ? launch_layer_bwd_warp<D, 7, true, true>(stream, a) : launch_layer_bwd_warp<D, 7, true, false>(stream, a);
+    return ln ? launch_layer_bwd_warp<D, 8, false, true>(stream, a) : launch_layer_bwd_warp<D, 8, false, false>(stream, a);
   }
 
   // persistent: every CTA of the fixed partial-sum grid writes its partials

@@ -307,6 +307,13 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_fwd_warp_kernel(const La
         row_load<D>(pei, a.x_ei + (r + 1) * D, lane);
         n0 = a.edges_in[r + 1]; n1 = a.edges_in[BC + r + 1]; n2 = a.edges_in[2 * BC + r + 1]; n3 = a.edges_in[3 * BC + r + 1];
       }
+      if (lane == 0) {        // DRAM latency runs two candidates ahead of the register loads (bulk L2 prefetch)
+        const long long pr = c + 2 < a.C ? r + 2 : (b + nwarps < B ? (b + nwarps) * a.C + (c + 2 - a.C) : -1);
+        if (pr >= 0) {
+          l2_prefetch(a.x_et + pr * D, D * 4);
+          l2_prefetch(a.x_ei + pr * D, D * 4);
+        }
+      }
       if (ln) {
         row_ln_gelu<D>(xet, s_gamma, s_beta, lane);
         row_ln_gelu<D>(xei, s_gamma, s_beta, lane);
@@ -550,6 +557,10 @@ __global__ void __launch_bounds__(NW * 32, 2) score_warp_kernel(const float* __r
       const long long r = b * C + c;
       RowT<D> e = hn;
       if (c + 1 < C) row_load<D>(hn, h_et + (r + 1) * D, lane);
+      if (lane == 0) {
+        const long long pr = c + 3 < C ? r + 3 : (b + nwarps < B ? (b + nwarps) * C + min(c + 3 - C, C - 1) : -1);
+        if (pr >= 0) l2_prefetch(h_et + pr * D, D * 4);
+      }
       row_ln_gelu<D>(e, s_gamma, s_beta, lane);
       float q = 0.f, d = 0.f;
 #pragma unroll
