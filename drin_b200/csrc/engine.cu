@@ -112,11 +112,6 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
   return DRIN_OK;
 }
 
-static int split_weight(cudaStream_t s, const float* w, const Planes& p, size_t n) {
-  if (!w) return fail(DRIN_ERR_ARG, "null parameter pointer");
-  return split_planes(s, w, p.hi, p.lo, (long long)n);
-}
-
 static Operand op(const Planes& p, long long rows, int cols, long long row_offset = 0) {
   Operand o;
   o.hi = p.hi + row_offset * cols;
@@ -138,17 +133,22 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
   const long long B = c.batch, C = c.candidates, BC = B * C;
   const int D = c.embed_dim, R = c.resnet_dim, L = c.gcn_layers;
 
-  // ---- weights -> bf16 planes (they change every optimizer step) ----
-  DRIN_TRY(split_weight(stream, p.w_mt, ws.w_mt, (size_t)D * D));
-  DRIN_TRY(split_weight(stream, p.w_et, ws.w_et, (size_t)D * D));
-  DRIN_TRY(split_weight(stream, p.w_mi, ws.w_mi, (size_t)D * R));
-  DRIN_TRY(split_weight(stream, p.w_ei, ws.w_ei, (size_t)D * R));
-  for (int l = 0; l < L; ++l) {
-    DRIN_TRY(split_weight(stream, p.layer[l].w_h, ws.layer[l].w_h, (size_t)D * D));
-    if (ws.layer[l].dyn) {
-      DRIN_TRY(split_weight(stream, p.layer[l].w_u, ws.layer[l].w_u, (size_t)D * D));
-      DRIN_TRY(split_weight(stream, p.layer[l].w_v, ws.layer[l].w_v, (size_t)D * D));
+  // ---- weights -> bf16 planes (they change every optimizer step): one launch for all matrices ----
+  {
+    SplitJobs jobs;
+    auto add = [&](const float* w, const Planes& pl, size_t n) { jobs.job[jobs.count++] = SplitJob{w, pl.hi, pl.lo, (long long)(n / 4)}; };
+    add(p.w_mt, ws.w_mt, (size_t)D * D);
+    add(p.w_et, ws.w_et, (size_t)D * D);
+    add(p.w_mi, ws.w_mi, (size_t)D * R);
+    add(p.w_ei, ws.w_ei, (size_t)D * R);
+    for (int l = 0; l < L; ++l) {
+      add(p.layer[l].w_h, ws.layer[l].w_h, (size_t)D * D);
+      if (ws.layer[l].dyn) {
+        add(p.layer[l].w_u, ws.layer[l].w_u, (size_t)D * D);
+        add(p.layer[l].w_v, ws.layer[l].w_v, (size_t)D * D);
+      }
     }
+    DRIN_TRY(split_planes_multi(stream, jobs));
   }
 
   // ---- front end: pooling, edges, projection operands ----

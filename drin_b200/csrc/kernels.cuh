@@ -1,5 +1,6 @@
 // Internal kernel-launcher declarations (host side).
 #pragma once
+#include "../../include/drin_b200.h"
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -23,6 +24,18 @@ int collect(double* ms, double* flops, double* bytes, long long* count);
 
 // elementwise.cu
 int split_planes(cudaStream_t stream, const float* x, bf16* hi, bf16* lo, long long n);
+struct SplitJob {
+  const float* x;
+  bf16* hi;
+  bf16* lo;        // null: plain bf16 rounding
+  long long n4;    // number of float4 (element count / 4)
+};
+struct SplitJobs {
+  static constexpr int MAX = 4 + 3 * DRIN_MAX_LAYERS;
+  SplitJob job[MAX];
+  int count = 0;
+};
+int split_planes_multi(cudaStream_t stream, const SplitJobs& jobs);   // one launch for all weight matrices of a step
 
 // frontend.cu
 struct FrontendArgs {
