@@ -7,8 +7,8 @@
 //     dL/ds[b,c] = k * ( A[b,c] - y[b,c] * N_b ),
 //        A[b,c] = #{ i : s[b,c] - p_i + margin > 0 },  N_b = #{ (b',c') : s[b',c'] - p_b + margin > 0 }.
 // Under data parallelism every rank holds the gathered global score matrix and evaluates its own rows.
-// Counts come from binary searches in sorted arrays (CUB radix sort of the positives and of the scores) and the
-// hinge sum is reduced in a fixed order in double precision, so the result is bit-reproducible.
+// Counts come from binary searches in the sorted positives (one small CUB radix sort) plus an integer histogram of the
+// global scores; the hinge sum is reduced in a fixed order in double precision, so the result is bit-reproducible.
 #include <cub/cub.cuh>
 
 #include "kernels.cuh"
@@ -17,35 +17,27 @@ namespace drin {
 
 static constexpr int TL_THREADS = 256;
 
-// O(N log N) evaluation: with the positives p sorted ascending (prefix sums P) and all global scores sorted,
+// O(N log N) evaluation with ONE small sort: with the positives p sorted ascending (prefix sums P),
 //   A[b,c]      = lower_bound(p_sorted, s + m)                       (# p_i < s + m)
 //   hinge[b,c]  = A * (s + m) - P[A]                                 (sum_i max(s - p_i + m, 0), in double)
-//   N_b         = n_scores - upper_bound(s_sorted, p_b - m)          (# s' > p_b - m)
-// so a rank pays O((B_loc C + B_glob C) log) instead of O(B_loc B_glob C) -- this is what keeps the loss flat when
-// the global batch grows with the number of GPUs.
+//   N_b         = # global scores s' with p_b < s' + m = sum_{j > pos_b} hist[j],
+//                 hist[j] = # global scores whose A equals j, pos_b = lower_bound(p_sorted, p_b)
+// so every rank sorts only the B_glob positives, bins all global scores with integer atomics (exact, order
+// independent) and pays O((B_glob C) log B_glob) -- flat when the global batch grows with the number of GPUs.
 struct TripletScratch {
   float* p;            // [B]
   float* p_sorted;     // [B]
   double* prefix;      // [B + 1]
-  float* s;            // [B * (C-1)] compacted global scores
-  float* s_sorted;     // [B * (C-1)]
-  int* n;              // [B]
+  int* hist;           // [B + 1]  -> inclusive cumulative counts after triplet_cum_kernel
   double* partial;     // [blocks]
   void* cub_temp;
   size_t cub_bytes;
 };
 
-static size_t cub_sort_bytes(size_t n) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const float*)nullptr, (float*)nullptr, (int)n);
-  return bytes;
-}
-
 static TripletScratch carve_triplet(void* scratch, int B, int C, size_t* bytes) {
   TripletScratch t;
   size_t off = 0;
   char* base = static_cast<char*>(scratch);
-  const size_t ns = (size_t)B * (C - 1);
   auto take = [&](size_t nbytes) {
     char* ptr = base ? base + off : nullptr;
     off = align_up(off + nbytes, 256);
@@ -54,12 +46,11 @@ static TripletScratch carve_triplet(void* scratch, int B, int C, size_t* bytes) 
   t.p = reinterpret_cast<float*>(take(sizeof(float) * B));
   t.p_sorted = reinterpret_cast<float*>(take(sizeof(float) * B));
   t.prefix = reinterpret_cast<double*>(take(sizeof(double) * (B + 1)));
-  t.s = reinterpret_cast<float*>(take(sizeof(float) * ns));
-  t.s_sorted = reinterpret_cast<float*>(take(sizeof(float) * ns));
-  t.n = reinterpret_cast<int*>(take(sizeof(int) * B));
+  t.hist = reinterpret_cast<int*>(take(sizeof(int) * (B + 1)));
   t.partial = reinterpret_cast<double*>(take(sizeof(double) * 65536));
-  t.cub_bytes = 2 * ns * sizeof(float) + (4u << 20);      // upper bound of the radix-sort temp storage (checked at run time)
+  t.cub_bytes = 2 * (size_t)B * sizeof(float) + (4u << 20);   // upper bound of the radix-sort temp storage (checked at run time)
   t.cub_temp = take(t.cub_bytes);
+  (void)C;
   if (bytes) *bytes = off;
   return t;
 }
@@ -70,24 +61,22 @@ size_t triplet_scratch_bytes(int B, int C) {
   return bytes;
 }
 
-// p[i] = sum_c s[i,c] y[i,c]; compact the real-candidate scores (drops the gold slot, utils.py:36-37)
+// p[i] = sum_c s[i,c] y[i,c] over the real candidates (the gold slot is sliced off, utils.py:36-37)
 __global__ void triplet_pos_kernel(const float* __restrict__ s, const unsigned char* __restrict__ y, int B, int C,
-                                   float* __restrict__ p, float* __restrict__ sc) {
+                                   float* __restrict__ p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float acc = 0.f;
-  for (int c = 0; c < C - 1; ++c) {
-    const float v = s[(long long)i * C + c];
-    acc += v * (float)y[(long long)i * (C - 1) + c];
-    sc[(long long)i * (C - 1) + c] = v;
-  }
+  for (int c = 0; c < C - 1; ++c) acc += s[(long long)i * C + c] * (float)y[(long long)i * (C - 1) + c];
   p[i] = acc;
 }
 
-// single-block exclusive prefix sums in double: prefix[j] = sum_{i<j} p_sorted[i], j = 0..B
-__global__ void __launch_bounds__(1024) triplet_prefix_kernel(const float* __restrict__ ps, int B, double* __restrict__ prefix) {
+// single-block exclusive prefix sums in double: prefix[j] = sum_{i<j} p_sorted[i], j = 0..B; also clears hist
+__global__ void __launch_bounds__(1024) triplet_prefix_kernel(const float* __restrict__ ps, int B, double* __restrict__ prefix,
+                                                               int* __restrict__ hist) {
   __shared__ double tot[1024];
   const int t = threadIdx.x;
+  for (int i = t; i <= B; i += 1024) hist[i] = 0;
   const int per = (B + 1023) / 1024;
   const int i0 = t * per, i1 = min(B, i0 + per);
   double acc = 0.0;
@@ -119,35 +108,34 @@ __device__ __forceinline__ int lower_bound_f(const float* __restrict__ a, int n,
   }
   return lo;
 }
-__device__ __forceinline__ int upper_bound_f(const float* __restrict__ a, int n, float v) {   // # a[i] <= v
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] <= v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
-// one thread per local score element
+// one thread per GLOBAL real-candidate score: bin it (hist[A] += 1, warp-aggregated integer atomics); the threads of
+// the local rows also emit k * A into dscores and their hinge term
 __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* __restrict__ s,
                                                                    const float* __restrict__ ps,
                                                                    const double* __restrict__ prefix, int B, int C,
                                                                    int row0, int rows, float margin, float k,
-                                                                   float* __restrict__ dscores,
+                                                                   float* __restrict__ dscores, int* __restrict__ hist,
                                                                    double* __restrict__ partial) {
   __shared__ double sred[TL_THREADS / 32];
-  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // over rows * (C-1)
-  const long long total = (long long)rows * (C - 1);
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // over B * (C-1)
+  const long long total = (long long)B * (C - 1);
   double hinge = 0.0;
+  int A = -1;
   if (e < total) {
-    const int bl = (int)(e / (C - 1));
-    const int c = (int)(e - (long long)bl * (C - 1));
-    const float sm = s[(long long)(row0 + bl) * C + c] + margin;
-    const int A = lower_bound_f(ps, B, sm);            // s - p_i + margin > 0  <=>  p_i < s + margin
-    hinge = (double)A * (double)sm - prefix[A];
-    if (sm != sm) hinge = (double)sm;                  // NaN scores poison the loss like upstream
-    dscores[(long long)bl * C + c] = k * (float)A;
+    const int b = (int)(e / (C - 1));
+    const int c = (int)(e - (long long)b * (C - 1));
+    const float sm = s[(long long)b * C + c] + margin;
+    A = lower_bound_f(ps, B, sm);                      // s - p_i + margin > 0  <=>  p_i < s + margin
+    if (b >= row0 && b < row0 + rows) {
+      hinge = (double)A * (double)sm - prefix[A];
+      if (sm != sm) hinge = (double)sm;                // NaN scores poison the loss like upstream
+      dscores[(long long)(b - row0) * C + c] = k * (float)A;
+    }
   }
+  // lanes with the same bin combine into one atomic (at init every score lands in the same bin)
+  const unsigned peers = __match_any_sync(0xffffffffu, A);
+  if (A >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + A, __popc(peers));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hinge += __shfl_xor_sync(0xffffffffu, hinge, o);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = hinge;
@@ -159,15 +147,34 @@ __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* 
   }
 }
 
-// N_b for the local rows: # global scores with s' > p_b - margin
-__global__ void triplet_n_kernel(const float* __restrict__ ss, long long ns, const float* __restrict__ p, int row0,
-                                 int rows, float margin, int* __restrict__ n) {
-  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bl >= rows) return;
-  n[row0 + bl] = (int)(ns - upper_bound_f(ss, (int)ns, p[row0 + bl] - margin));
+// single block: hist[j] -> inclusive cumulative counts cum[j] = sum_{i <= j} hist[i], j = 0..B
+__global__ void __launch_bounds__(1024) triplet_cum_kernel(int* __restrict__ hist, int B) {
+  __shared__ int tot[1024];
+  const int t = threadIdx.x, n = B + 1;
+  const int per = (n + 1023) / 1024;
+  const int i0 = min(n, t * per), i1 = min(n, i0 + per);
+  int acc = 0;
+  for (int i = i0; i < i1; ++i) acc += hist[i];
+  tot[t] = acc;
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const int v = tot[i];
+      tot[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  int run = tot[t];
+  for (int i = i0; i < i1; ++i) {
+    run += hist[i];
+    hist[i] = run;
+  }
 }
 
-__global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const int* __restrict__ n, int C, int row0,
+__global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const float* __restrict__ p,
+                                      const float* __restrict__ ps, const int* __restrict__ cum, int B, int C, int row0,
                                       int rows, float k, float* __restrict__ dscores, const double* __restrict__ partial,
                                       int nblocks, float* __restrict__ loss) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // over rows * C
@@ -176,10 +183,14 @@ __global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const
     if (c == C - 1) {
       dscores[e] = 0.f;                                     // the gold slot is sliced off (utils.py:36-37)
     } else if (y[(long long)(row0 + bl) * (C - 1) + c]) {
-      dscores[e] -= k * (float)y[(long long)(row0 + bl) * (C - 1) + c] * (float)n[row0 + bl];
+      // N_b = # global scores with p_b < s' + margin = total - cum[pos_b]
+      const int pos = lower_bound_f(ps, B, p[row0 + bl]);
+      const int n_b = cum[B] - cum[pos];
+      dscores[e] -= k * (float)y[(long long)(row0 + bl) * (C - 1) + c] * (float)n_b;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // only the blocks that cover local rows hold non-zero hinge partials; all are summed in block order
     double t = 0.0;
     for (int i = 0; i < nblocks; ++i) t += partial[i];
     loss[0] = (float)(t * (double)k);
@@ -196,7 +207,7 @@ int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* 
   TripletScratch t = carve_triplet(scratch, B, C, nullptr);
   const long long ns = (long long)B * (C - 1);
   const float k = (float)(1.0 / ((double)B * (double)B * (double)(C - 1)));
-  triplet_pos_kernel<<<(B + 255) / 256, 256, 0, stream>>>(scores, labels, B, C, t.p, t.s);
+  triplet_pos_kernel<<<(B + 255) / 256, 256, 0, stream>>>(scores, labels, B, C, t.p);
   DRIN_LAUNCH_CHECK();
   size_t need = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, need, t.p, t.p_sorted, B);
@@ -204,24 +215,18 @@ int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* 
   size_t tmp = t.cub_bytes;
   DRIN_CUDA(cub::DeviceRadixSort::SortKeys(t.cub_temp, tmp, t.p, t.p_sorted, B, 0, 32, stream));
   count_launch();
-  cub::DeviceRadixSort::SortKeys(nullptr, need, t.s, t.s_sorted, (int)ns);
-  if (need > t.cub_bytes) return fail(DRIN_ERR_WORKSPACE, "triplet_loss: sort temp %zu > %zu", need, t.cub_bytes);
-  tmp = t.cub_bytes;
-  DRIN_CUDA(cub::DeviceRadixSort::SortKeys(t.cub_temp, tmp, t.s, t.s_sorted, (int)ns, 0, 32, stream));
-  count_launch();
-  triplet_prefix_kernel<<<1, 1024, 0, stream>>>(t.p_sorted, B, t.prefix);
+  triplet_prefix_kernel<<<1, 1024, 0, stream>>>(t.p_sorted, B, t.prefix, t.hist);
   DRIN_LAUNCH_CHECK();
-  const long long local = (long long)rows * (C - 1);
-  const int cblocks = (int)((local + TL_THREADS - 1) / TL_THREADS);
-  if (cblocks > 65536) return fail(DRIN_ERR_ARG, "triplet_loss: too many local scores (%lld)", local);
+  const int cblocks = (int)((ns + TL_THREADS - 1) / TL_THREADS);
+  if (cblocks > 65536) return fail(DRIN_ERR_ARG, "triplet_loss: too many scores (%lld)", ns);
   triplet_count_kernel<<<cblocks, TL_THREADS, 0, stream>>>(scores, t.p_sorted, t.prefix, B, C, row0, rows, margin, k,
-                                                           dscores, t.partial);
+                                                           dscores, t.hist, t.partial);
   DRIN_LAUNCH_CHECK();
-  triplet_n_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(t.s_sorted, ns, t.p, row0, rows, margin, t.n);
+  triplet_cum_kernel<<<1, 1024, 0, stream>>>(t.hist, B);
   DRIN_LAUNCH_CHECK();
   const long long fe = (long long)rows * C;
-  triplet_finish_kernel<<<(int)((fe + 255) / 256), 256, 0, stream>>>(labels, t.n, C, row0, rows, k, dscores, t.partial,
-                                                                     cblocks, loss);
+  triplet_finish_kernel<<<(int)((fe + 255) / 256), 256, 0, stream>>>(labels, t.p, t.p_sorted, t.hist, B, C, row0, rows, k,
+                                                                     dscores, t.partial, cblocks, loss);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }
