@@ -36,7 +36,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     files = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "drin_b200.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # relative names: the tree may live anywhere (gpurun copies it)
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -51,10 +51,26 @@ def is_fresh() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile if the sources changed.  Safe under torchrun: ranks serialise on a lock file, objects go to a
+    per-process directory and the library is moved into place atomically."""
     if not force and is_fresh():
         return LIB_PATH
+    import fcntl
+
+    os.makedirs(os.path.join(PKG_DIR, "build"), exist_ok=True)
+    with open(os.path.join(PKG_DIR, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():          # another rank built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     objs = []
-    obj_dir = os.path.join(PKG_DIR, "build")
+    obj_dir = os.path.join(PKG_DIR, "build", f"obj{os.getpid()}")
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in sources():
@@ -70,12 +86,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
         if verbose and out:
             print(out, file=sys.stderr)
-    link = [_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    tmp_lib = os.path.join(obj_dir, "libdrin_b200.so")
+    link = [_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    with open(STAMP_PATH, "w") as fh:
+    os.replace(tmp_lib, LIB_PATH)
+    with open(STAMP_PATH + ".tmp", "w") as fh:
         fh.write(_digest())
+    os.replace(STAMP_PATH + ".tmp", STAMP_PATH)
+    shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB_PATH
 
 
