@@ -74,30 +74,21 @@ __global__ void triplet_pos_kernel(const float* __restrict__ s, const unsigned c
 // single-block exclusive prefix sums in double: prefix[j] = sum_{i<j} p_sorted[i], j = 0..B; also clears hist
 __global__ void __launch_bounds__(1024) triplet_prefix_kernel(const float* __restrict__ ps, int B, double* __restrict__ prefix,
                                                                int* __restrict__ hist) {
-  __shared__ double tot[1024];
+  typedef cub::BlockScan<double, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
   const int t = threadIdx.x;
   for (int i = t; i <= B; i += 1024) hist[i] = 0;
   const int per = (B + 1023) / 1024;
-  const int i0 = t * per, i1 = min(B, i0 + per);
+  const int i0 = min(B, t * per), i1 = min(B, i0 + per);
   double acc = 0.0;
   for (int i = i0; i < i1; ++i) acc += (double)ps[i];
-  tot[t] = acc;
-  __syncthreads();
-  if (t == 0) {
-    double run = 0.0;
-    for (int i = 0; i < 1024; ++i) {
-      const double v = tot[i];
-      tot[i] = run;
-      run += v;
-    }
-  }
-  __syncthreads();
-  double run = tot[t];
+  double run;
+  Scan(tmp).ExclusiveSum(acc, run);          // fixed tree order: deterministic
   for (int i = i0; i < i1; ++i) {
     prefix[i] = run;
     run += (double)ps[i];
   }
-  if (i0 < B && i1 == B) prefix[B] = run;
+  if (i0 < B && i1 == B) prefix[B] = run;      // the thread that owns the last element
 }
 
 __device__ __forceinline__ int lower_bound_f(const float* __restrict__ a, int n, float v) {   // # a[i] < v
@@ -149,24 +140,15 @@ __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* 
 
 // single block: hist[j] -> inclusive cumulative counts cum[j] = sum_{i <= j} hist[i], j = 0..B
 __global__ void __launch_bounds__(1024) triplet_cum_kernel(int* __restrict__ hist, int B) {
-  __shared__ int tot[1024];
+  typedef cub::BlockScan<int, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
   const int t = threadIdx.x, n = B + 1;
   const int per = (n + 1023) / 1024;
   const int i0 = min(n, t * per), i1 = min(n, i0 + per);
   int acc = 0;
   for (int i = i0; i < i1; ++i) acc += hist[i];
-  tot[t] = acc;
-  __syncthreads();
-  if (t == 0) {
-    int run = 0;
-    for (int i = 0; i < 1024; ++i) {
-      const int v = tot[i];
-      tot[i] = run;
-      run += v;
-    }
-  }
-  __syncthreads();
-  int run = tot[t];
+  int run;
+  Scan(tmp).ExclusiveSum(acc, run);
   for (int i = i0; i < i1; ++i) {
     run += hist[i];
     hist[i] = run;
