@@ -160,3 +160,45 @@ def test_fused_adam_matches_torch_adam():
         opt_ref.step()
     for n, p, r in zip(names, model.parameters(), ref):
         assert torch.allclose(p.detach(), r.detach(), rtol=2e-6, atol=1e-8), n
+
+
+@pytest.mark.parametrize("variant", [-1, 1], ids=["auto", "warp-kernels"])
+@pytest.mark.parametrize("dataset,B,cands,layers,kw", [("wikidiverse", 9, 10, 2, {}), ("wikidiverse", 8, 10, 3, {}),
+                                                       ("wikimel", 3, 100, 2, {})])
+def test_forward_intermediates_stage_by_stage(dataset, B, cands, layers, kw, variant):
+    """Every stage of Model.forward against the oracle through the workspace test hook (drin_debug_buffer):
+    projections x0 (model.py:26-46), edge list (model.py:201-204), per layer the activated vertices
+    gelu(LN(h)) (model.py:128) and the dynamic edge update (model.py:131-134), then the scores."""
+    import torch.nn.functional as F
+
+    from drin_b200.synthetic import spread_weights
+    for name in ("score_fwd_variant", "layer_fwd_variant"):
+        _lib.check(_lib.load().drin_debug_option(name.encode(), C.c_int32(variant)), "drin_debug_option")
+    try:
+        cfg = O.DrinConfig(num_candidates_model=cands + 1, num_gcn_layers=layers)
+        batch = make_batch(dataset, B, 31, cands, **kw)
+        sd = spread_weights(O.init_state(cfg, 0))
+        V = O.vertex_encode(sd, batch[:-1])
+        tt, ii = O.edge_encode(batch[:-1])
+        Ed = [tt, batch[13] / 100, batch[12] / 100, ii]
+        eng = E.Engine(layers)
+        scores, ctx = eng.forward([t.cuda() for t in batch[:-1]], {k: v.cuda() for k, v in sd.items()}, training=False)
+        x0 = torch.cat([V[0], V[1], V[2].flatten(0, 1), V[3].flatten(0, 1)])
+        assert rel_err(eng.debug_buffer(ctx, "x0").cpu(), x0) < 1e-5
+        assert rel_err(eng.debug_buffer(ctx, "edges0").cpu(), torch.stack([e.flatten() for e in Ed])) < 2e-6
+        Vl, El = V, Ed
+        for l in range(layers):
+            Vl, El = O.gcn_layer(sd, l, cfg, Vl, El)
+            h = eng.debug_buffer(ctx, "h", l).cpu()
+            k = O.gcn_keys(l)
+            act = F.gelu(F.layer_norm(h, (h.shape[-1],), sd[k["ln_w"]], sd[k["ln_b"]], 1e-5))
+            if l < layers - 1:
+                want = torch.cat([Vl[0], Vl[1], Vl[2].flatten(0, 1), Vl[3].flatten(0, 1)])
+                assert rel_err(eng.debug_buffer(ctx, "edges_out", l).cpu(), torch.stack([e.flatten() for e in El])) < 1e-5
+            else:
+                want = torch.cat([Vl[0], Vl[2].flatten(0, 1)])       # the last layer only updates mt / et
+            assert rel_err(act, want) < 2e-5, l
+        assert rel_err(scores.cpu(), O.cosine(Vl[0].unsqueeze(1), Vl[2])) < 1e-5
+    finally:
+        for name in ("score_fwd_variant", "layer_fwd_variant"):
+            _lib.check(_lib.load().drin_debug_option(name.encode(), C.c_int32(-1)), "drin_debug_option")
