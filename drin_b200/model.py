@@ -173,8 +173,14 @@ class Model(nn.Module):
 
     @property
     def flat_grads(self) -> torch.Tensor:
+        return self.flat_grads_bucket[:self._flat.numel()]
+
+    @property
+    def flat_grads_bucket(self) -> torch.Tensor:
+        """The all-reduce bucket: the flat gradient buffer plus 4 trailing floats; the data-parallel trainer puts its
+        share of the loss in the first of them so gradients and loss are summed by ONE collective."""
         if self._flat_grad is None or self._flat_grad.device != self._flat.device:
-            self._flat_grad = torch.zeros_like(self._flat)
+            self._flat_grad = torch.zeros(self._flat.numel() + 4, dtype=torch.float32, device=self._flat.device)
         return self._flat_grad
 
     def _grad_views(self, flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:

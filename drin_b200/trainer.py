@@ -8,7 +8,8 @@ Data parallelism: mentions are sharded across ranks, parameters r
     gradient of the GLOBAL loss for its own rows.  The result equals the reference run at the global
     batch size, not at the local one.
   * Parameter gradients are summed with ONE all-reduce over the flat gradient buffer (26.8 MB live,
-    31.5 MB total) -- no averaging: the 1/B_glob^2 normalisation is already in dL/dscores.
+    31.5 MB total) -- no averaging: the 1/B_glob^2 normalisation is already in dL/dscores.  The per-rank loss
+    shares travel in the same bucket, and the labels travel with the scores: two collectives per step in total.
   * Ranking needs no communication beyond a final gather of the scores.
 """
 from __future__ import annotations
@@ -37,6 +38,26 @@ def gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def gather_scores_and_labels(scores: torch.Tensor, labels: torch.Tensor, group=None):
+    """Global ``[B_glob, C]`` scores and ``[B_glob, C-1]`` uint8 labels from the local shards with ONE all-gather: the
+    one-hot labels ride along with the scores as 0/1 floats."""
+    if not _dist_on(group):
+        return scores, labels.to(torch.uint8)
+    Cn = scores.shape[1]
+    packed = gather_rows(torch.cat([scores, labels.to(scores.dtype)], dim=1), group)
+    return packed[:, :Cn].contiguous(), packed[:, Cn:].to(torch.uint8)
+
+
+def reduce_grads_and_loss(bucket: torch.Tensor, n: int, loss_share: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the flat gradients (``bucket[:n]``) and the per-rank loss shares over the ranks with ONE all-reduce: the
+    loss share travels in ``bucket[n]``.  No averaging: 1/B_glob^2 is already in dL/dscores."""
+    if not _dist_on(group):
+        return loss_share
+    bucket[n:n + 1].copy_(loss_share.reshape(1))
+    dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+    return bucket[n:n + 1].clone()
+
+
 class Trainer:
     def __init__(self, model: Model, lr: float = 1e-3, margin: float = 0.25, group=None):
         self.model, self.margin, self.group = model, float(margin), group
@@ -63,13 +84,11 @@ class Trainer:
         scores, ctx = m._engine.forward(inputs, params, training=True, num_candidates_model=m.num_candidates_model)
         self.last_scores = scores
         b_loc = scores.shape[0]
-        scores_all = gather_rows(scores, self.group)
-        labels_all = gather_rows(y.to(torch.uint8), self.group)
+        scores_all, labels_all = gather_scores_and_labels(scores, y, self.group)
         loss, dscores = triplet_loss_sharded(scores_all, labels_all, self.margin, self.rank * b_loc, b_loc)
         m._engine.backward(ctx, inputs, params, dscores, m._grad_views())
-        if _dist_on(self.group):
-            dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)   # one 31.5 MB bucket
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        # 31.5 MB of gradients + this rank's share of the loss in the bucket's tail
+        loss = reduce_grads_and_loss(m.flat_grads_bucket, m.flat_params.numel(), loss, self.group)
         return loss.reshape(())
 
     def step(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -1,7 +1,8 @@
 """World-size-2 check of the data-parallel protocol on CPU (gloo): shard the mentions, all-gather the
 scores BEFORE the loss (it couples the whole batch), take the gradient of the GLOBAL loss for the local
 rows, sum parameter gradients with one flat all-reduce -- the result must equal the full-batch reference
-step.  Host logic under test: drin_b200.trainer.gather_rows and the no-averaging convention; the per-rank
+step.  Host logic under test: drin_b200.trainer's collective helpers (one packed all-gather, one bucket all-reduce) and
+the no-averaging convention; the per-rank
 arithmetic is done by the CPU oracle (the CUDA kernels are covered by the -m gpu tests)."""
 import os
 import socket
@@ -12,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from drin_b200.synthetic import make_batch, spread_weights
-from drin_b200.trainer import gather_rows
+from drin_b200.trainer import gather_rows, gather_scores_and_labels, reduce_grads_and_loss
 from oracle import drin_oracle as O
 
 
@@ -34,15 +35,15 @@ def _worker(rank, world, port, out):
     shard = [t[rank * bl:(rank + 1) * bl] for t in batch]
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     scores = O.forward(leaves, shard[:-1], cfg)
-    scores_all = gather_rows(scores.detach(), None)
-    labels_all = gather_rows(shard[-1], None)
+    scores_all, labels_all = gather_scores_and_labels(scores.detach(), shard[-1], None)     # ONE all-gather
+    assert labels_all.dtype == torch.uint8 and torch.equal(labels_all, batch[-1])
     share, dscores = O.triplet_sharded(scores_all, labels_all, cfg.triplet_margin, rank * bl, bl)
     scores.backward(dscores)
     live = [k for k in sd if leaves[k].grad is not None]
     flat = torch.cat([leaves[k].grad.flatten() for k in live])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)          # summed, NOT averaged: 1/B_glob^2 is already in dscores
-    loss = share.clone()
-    dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    bucket = torch.cat([flat, torch.zeros(4)])            # gradients + loss share: ONE all-reduce, summed NOT averaged
+    loss = reduce_grads_and_loss(bucket, flat.numel(), share, None)
+    flat = bucket[:flat.numel()]
     if rank == 0:
         s_ref, l_ref, g_ref = O.train_step_grads(sd, batch[:-1], batch[-1], cfg)
         ref_flat = torch.cat([g_ref[k].flatten() for k in live])
