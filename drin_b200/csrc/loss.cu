@@ -7,8 +7,8 @@
 //     dL/ds[b,c] = k * ( A[b,c] - y[b,c] * N_b ),
 //        A[b,c] = #{ i : s[b,c] - p_i + margin > 0 },  N_b = #{ (b',c') : s[b',c'] - p_b + margin > 0 }.
 // Under data parallelism every rank holds the gathered global score matrix and evaluates its own rows.
-// Counts come from binary searches in the sorted positives (one small CUB radix sort) plus an integer histogram of the
-// global scores; the hinge sum is reduced in a fixed order in double precision, so the result is bit-reproducible.
+// Counts come from binary searches in segment-sorted positives plus integer histograms of the global scores; the
+// hinge sum is reduced in a fixed order in double precision, so the result is bit-reproducible.
 #include <cub/cub.cuh>
 
 #include "kernels.cuh"
@@ -17,39 +17,42 @@ namespace drin {
 
 static constexpr int TL_THREADS = 256;
 
-// O(N log N) evaluation with ONE small sort: with the positives p sorted ascending (prefix sums P),
-//   A[b,c]      = lower_bound(p_sorted, s + m)                       (# p_i < s + m)
-//   hinge[b,c]  = A * (s + m) - P[A]                                 (sum_i max(s - p_i + m, 0), in double)
-//   N_b         = # global scores s' with p_b < s' + m = sum_{j > pos_b} hist[j],
-//                 hist[j] = # global scores whose A equals j, pos_b = lower_bound(p_sorted, p_b)
-// so every rank sorts only the B_glob positives, bins all global scores with integer atomics (exact, order
-// independent) and pays O((B_glob C) log B_glob) -- flat when the global batch grows with the number of GPUs.
+// O(N log N) evaluation without a global sort.  The B_glob positives are cut into segments of TL_SEG = 4096 (a rank's
+// shard is one segment at the benchmark size) and every segment is sorted by ONE CTA (cub::BlockRadixSort), with its
+// prefix sums P_g in double.  For a score s (m = margin):
+//   A[b,c]      = sum_g lower_bound(seg_g, s + m)                    (# p_i < s + m)
+//   hinge[b,c]  = sum_g ( A_g * (s + m) - P_g[A_g] )                 (sum_i max(s - p_i + m, 0), in double)
+//   N_b         = # global scores s' with p_b < s' + m = sum_{j > pos_b} hist_g[j] for the segment g that holds p_b,
+//                 hist_g[j] = # global scores whose lower_bound in seg_g equals j, pos_b = lower_bound(seg_g, p_b)
+// so a rank bins all global scores only against its OWN segments (integer atomics: exact, order independent) and
+// searches all segments only for its own scores: five launches whatever the number of GPUs.
+static constexpr int TL_SEG = 4096;
+static constexpr int TL_SORT_THREADS = 1024;
+static constexpr int TL_SORT_ITEMS = TL_SEG / TL_SORT_THREADS;
+
 struct TripletScratch {
   float* p;            // [B]
-  float* p_sorted;     // [B]
-  double* prefix;      // [B + 1]
-  int* hist;           // [B + 1]  -> inclusive cumulative counts after triplet_cum_kernel
+  float* p_sorted;     // [S][TL_SEG]       sorted per segment, padded with +inf
+  double* prefix;      // [S][TL_SEG + 1]   exclusive prefix sums per segment
+  int* hist;           // [S][TL_SEG + 1]   -> inclusive cumulative counts after triplet_cum_kernel (local segments)
   double* partial;     // [blocks]
-  void* cub_temp;
-  size_t cub_bytes;
 };
 
 static TripletScratch carve_triplet(void* scratch, int B, int C, size_t* bytes) {
   TripletScratch t;
   size_t off = 0;
   char* base = static_cast<char*>(scratch);
+  const size_t S = ((size_t)B + TL_SEG - 1) / TL_SEG;
   auto take = [&](size_t nbytes) {
     char* ptr = base ? base + off : nullptr;
     off = align_up(off + nbytes, 256);
     return ptr;
   };
   t.p = reinterpret_cast<float*>(take(sizeof(float) * B));
-  t.p_sorted = reinterpret_cast<float*>(take(sizeof(float) * B));
-  t.prefix = reinterpret_cast<double*>(take(sizeof(double) * (B + 1)));
-  t.hist = reinterpret_cast<int*>(take(sizeof(int) * (B + 1)));
+  t.p_sorted = reinterpret_cast<float*>(take(sizeof(float) * S * TL_SEG));
+  t.prefix = reinterpret_cast<double*>(take(sizeof(double) * S * (TL_SEG + 1)));
+  t.hist = reinterpret_cast<int*>(take(sizeof(int) * S * (TL_SEG + 1)));
   t.partial = reinterpret_cast<double*>(take(sizeof(double) * 65536));
-  t.cub_bytes = 2 * (size_t)B * sizeof(float) + (4u << 20);   // upper bound of the radix-sort temp storage (checked at run time)
-  t.cub_temp = take(t.cub_bytes);
   (void)C;
   if (bytes) *bytes = off;
   return t;
@@ -71,24 +74,49 @@ __global__ void triplet_pos_kernel(const float* __restrict__ s, const unsigned c
   p[i] = acc;
 }
 
-// single-block exclusive prefix sums in double: prefix[j] = sum_{i<j} p_sorted[i], j = 0..B; also clears hist
-__global__ void __launch_bounds__(1024) triplet_prefix_kernel(const float* __restrict__ ps, int B, double* __restrict__ prefix,
-                                                               int* __restrict__ hist) {
-  typedef cub::BlockScan<double, 1024> Scan;
-  __shared__ typename Scan::TempStorage tmp;
-  const int t = threadIdx.x;
-  for (int i = t; i <= B; i += 1024) hist[i] = 0;
-  const int per = (B + 1023) / 1024;
-  const int i0 = min(B, t * per), i1 = min(B, i0 + per);
-  double acc = 0.0;
-  for (int i = i0; i < i1; ++i) acc += (double)ps[i];
-  double run;
-  Scan(tmp).ExclusiveSum(acc, run);          // fixed tree order: deterministic
-  for (int i = i0; i < i1; ++i) {
-    prefix[i] = run;
-    run += (double)ps[i];
+// one CTA per segment: sort its positives, exclusive prefix sums in double, clear its histogram
+__global__ void __launch_bounds__(TL_SORT_THREADS) triplet_segsort_kernel(const float* __restrict__ p, int B,
+                                                                          float* __restrict__ p_sorted,
+                                                                          double* __restrict__ prefix,
+                                                                          int* __restrict__ hist) {
+  typedef cub::BlockRadixSort<float, TL_SORT_THREADS, TL_SORT_ITEMS> Sort;
+  typedef cub::BlockScan<double, TL_SORT_THREADS> Scan;
+  __shared__ union {
+    typename Sort::TempStorage sort;
+    typename Scan::TempStorage scan;
+  } tmp;
+  const int g = blockIdx.x, t = threadIdx.x;
+  const int base = g * TL_SEG, n = min(TL_SEG, B - base);
+  float keys[TL_SORT_ITEMS];
+#pragma unroll
+  for (int i = 0; i < TL_SORT_ITEMS; ++i) {
+    const int idx = t * TL_SORT_ITEMS + i;
+    keys[i] = idx < n ? p[base + idx] : __int_as_float(0x7f800000);     // +inf padding sorts last
   }
-  if (i0 < B && i1 == B) prefix[B] = run;      // the thread that owns the last element
+  Sort(tmp.sort).Sort(keys);                                             // blocked arrangement, ascending
+  __syncthreads();
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < TL_SORT_ITEMS; ++i) {
+    const int idx = t * TL_SORT_ITEMS + i;
+    p_sorted[(long long)g * TL_SEG + idx] = keys[i];
+    if (idx < n) acc += (double)keys[i];
+  }
+  double run;
+  Scan(tmp.scan).ExclusiveSum(acc, run);                                 // fixed tree order: deterministic
+  double* pf = prefix + (long long)g * (TL_SEG + 1);
+#pragma unroll
+  for (int i = 0; i < TL_SORT_ITEMS; ++i) {
+    const int idx = t * TL_SORT_ITEMS + i;
+    if (idx < n) {
+      pf[idx] = run;
+      run += (double)keys[i];
+      if (idx == n - 1) pf[n] = run;
+    }
+  }
+  if (n == 0 && t == 0) pf[0] = 0.0;
+  int* h = hist + (long long)g * (TL_SEG + 1);
+  for (int i = t; i <= TL_SEG; i += TL_SORT_THREADS) h[i] = 0;
 }
 
 __device__ __forceinline__ int lower_bound_f(const float* __restrict__ a, int n, float v) {   // # a[i] < v
@@ -100,33 +128,51 @@ __device__ __forceinline__ int lower_bound_f(const float* __restrict__ a, int n,
   return lo;
 }
 
-// one thread per GLOBAL real-candidate score: bin it (hist[A] += 1, warp-aggregated integer atomics); the threads of
-// the local rows also emit k * A into dscores and their hinge term
+// one thread per GLOBAL real-candidate score: bin it against the segments [g0, g1] that hold the local rows
+// (hist_g[A_g] += 1, warp-aggregated integer atomics); the threads of the local rows also search the other segments
+// and emit k * A into dscores and their hinge term
 __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* __restrict__ s,
                                                                    const float* __restrict__ ps,
                                                                    const double* __restrict__ prefix, int B, int C,
-                                                                   int row0, int rows, float margin, float k,
+                                                                   int row0, int rows, int g0, int g1, int S,
+                                                                   float margin, float k,
                                                                    float* __restrict__ dscores, int* __restrict__ hist,
                                                                    double* __restrict__ partial) {
   __shared__ double sred[TL_THREADS / 32];
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // over B * (C-1)
   const long long total = (long long)B * (C - 1);
+  const bool valid = e < total;
   double hinge = 0.0;
-  int A = -1;
-  if (e < total) {
-    const int b = (int)(e / (C - 1));
-    const int c = (int)(e - (long long)b * (C - 1));
-    const float sm = s[(long long)b * C + c] + margin;
-    A = lower_bound_f(ps, B, sm);                      // s - p_i + margin > 0  <=>  p_i < s + margin
-    if (b >= row0 && b < row0 + rows) {
-      hinge = (double)A * (double)sm - prefix[A];
-      if (sm != sm) hinge = (double)sm;                // NaN scores poison the loss like upstream
-      dscores[(long long)(b - row0) * C + c] = k * (float)A;
+  int b = 0, c = 0;
+  float sm = 0.f;
+  if (valid) {
+    b = (int)(e / (C - 1));
+    c = (int)(e - (long long)b * (C - 1));
+    sm = s[(long long)b * C + c] + margin;
+  }
+  const bool local = valid && b >= row0 && b < row0 + rows;
+  int A = 0;
+  for (int g = 0; g < S; ++g) {
+    const bool mine = g >= g0 && g <= g1;
+    if (!mine && !__any_sync(0xffffffffu, local)) continue;                  // warp-uniform skip
+    int j = -1;
+    if (valid && (mine || local)) {
+      const int n = min(TL_SEG, B - g * TL_SEG);
+      j = lower_bound_f(ps + (long long)g * TL_SEG, n, sm);              // s - p_i + margin > 0  <=>  p_i < s + margin
+      if (local) {
+        A += j;
+        hinge += (double)j * (double)sm - prefix[(long long)g * (TL_SEG + 1) + j];
+      }
+    }
+    if (mine) {   // lanes with the same bin combine into one atomic (at init every score lands in the same bin)
+      const unsigned peers = __match_any_sync(0xffffffffu, j);
+      if (j >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + (long long)g * (TL_SEG + 1) + j, __popc(peers));
     }
   }
-  // lanes with the same bin combine into one atomic (at init every score lands in the same bin)
-  const unsigned peers = __match_any_sync(0xffffffffu, A);
-  if (A >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + A, __popc(peers));
+  if (local) {
+    if (sm != sm) hinge = (double)sm;                  // NaN scores poison the loss like upstream
+    dscores[(long long)(b - row0) * C + c] = k * (float)A;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hinge += __shfl_xor_sync(0xffffffffu, hinge, o);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = hinge;
@@ -138,20 +184,21 @@ __global__ void __launch_bounds__(TL_THREADS) triplet_count_kernel(const float* 
   }
 }
 
-// single block: hist[j] -> inclusive cumulative counts cum[j] = sum_{i <= j} hist[i], j = 0..B
-__global__ void __launch_bounds__(1024) triplet_cum_kernel(int* __restrict__ hist, int B) {
+// one CTA per local segment: hist_g[j] -> inclusive cumulative counts
+__global__ void __launch_bounds__(1024) triplet_cum_kernel(int* __restrict__ hist, int g0) {
   typedef cub::BlockScan<int, 1024> Scan;
   __shared__ typename Scan::TempStorage tmp;
-  const int t = threadIdx.x, n = B + 1;
+  int* h = hist + (long long)(g0 + blockIdx.x) * (TL_SEG + 1);
+  const int t = threadIdx.x, n = TL_SEG + 1;
   const int per = (n + 1023) / 1024;
   const int i0 = min(n, t * per), i1 = min(n, i0 + per);
   int acc = 0;
-  for (int i = i0; i < i1; ++i) acc += hist[i];
+  for (int i = i0; i < i1; ++i) acc += h[i];
   int run;
   Scan(tmp).ExclusiveSum(acc, run);
   for (int i = i0; i < i1; ++i) {
-    run += hist[i];
-    hist[i] = run;
+    run += h[i];
+    h[i] = run;
   }
 }
 
@@ -165,10 +212,13 @@ __global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const
     if (c == C - 1) {
       dscores[e] = 0.f;                                     // the gold slot is sliced off (utils.py:36-37)
     } else if (y[(long long)(row0 + bl) * (C - 1) + c]) {
-      // N_b = # global scores with p_b < s' + margin = total - cum[pos_b]
-      const int pos = lower_bound_f(ps, B, p[row0 + bl]);
-      const int n_b = cum[B] - cum[pos];
-      dscores[e] -= k * (float)y[(long long)(row0 + bl) * (C - 1) + c] * (float)n_b;
+      // N_b = # global scores with p_b < s' + margin, from the cumulative histogram of the segment that holds p_b
+      const int b = row0 + bl, g = b / TL_SEG;
+      const int n = min(TL_SEG, B - g * TL_SEG);
+      const int* cg = cum + (long long)g * (TL_SEG + 1);
+      const int pos = lower_bound_f(ps + (long long)g * TL_SEG, n, p[b]);
+      const int n_b = cg[TL_SEG] - cg[pos];
+      dscores[e] -= k * (float)y[(long long)b * (C - 1) + c] * (float)n_b;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -188,23 +238,19 @@ int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* 
   if ((long long)B * (C - 1) > 0x7fffffffLL) return fail(DRIN_ERR_ARG, "triplet_loss: batch too large");
   TripletScratch t = carve_triplet(scratch, B, C, nullptr);
   const long long ns = (long long)B * (C - 1);
+  const int S = (B + TL_SEG - 1) / TL_SEG;
+  const int g0 = row0 / TL_SEG, g1 = (row0 + rows - 1) / TL_SEG;       // segments that hold the local rows
   const float k = (float)(1.0 / ((double)B * (double)B * (double)(C - 1)));
   triplet_pos_kernel<<<(B + 255) / 256, 256, 0, stream>>>(scores, labels, B, C, t.p);
   DRIN_LAUNCH_CHECK();
-  size_t need = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, need, t.p, t.p_sorted, B);
-  if (need > t.cub_bytes) return fail(DRIN_ERR_WORKSPACE, "triplet_loss: sort temp %zu > %zu", need, t.cub_bytes);
-  size_t tmp = t.cub_bytes;
-  DRIN_CUDA(cub::DeviceRadixSort::SortKeys(t.cub_temp, tmp, t.p, t.p_sorted, B, 0, 32, stream));
-  count_launch();
-  triplet_prefix_kernel<<<1, 1024, 0, stream>>>(t.p_sorted, B, t.prefix, t.hist);
+  triplet_segsort_kernel<<<S, TL_SORT_THREADS, 0, stream>>>(t.p, B, t.p_sorted, t.prefix, t.hist);
   DRIN_LAUNCH_CHECK();
   const int cblocks = (int)((ns + TL_THREADS - 1) / TL_THREADS);
   if (cblocks > 65536) return fail(DRIN_ERR_ARG, "triplet_loss: too many scores (%lld)", ns);
-  triplet_count_kernel<<<cblocks, TL_THREADS, 0, stream>>>(scores, t.p_sorted, t.prefix, B, C, row0, rows, margin, k,
-                                                           dscores, t.hist, t.partial);
+  triplet_count_kernel<<<cblocks, TL_THREADS, 0, stream>>>(scores, t.p_sorted, t.prefix, B, C, row0, rows, g0, g1, S, margin,
+                                                           k, dscores, t.hist, t.partial);
   DRIN_LAUNCH_CHECK();
-  triplet_cum_kernel<<<1, 1024, 0, stream>>>(t.hist, B);
+  triplet_cum_kernel<<<g1 - g0 + 1, 1024, 0, stream>>>(t.hist, g0);
   DRIN_LAUNCH_CHECK();
   const long long fe = (long long)rows * C;
   triplet_finish_kernel<<<(int)((fe + 255) / 256), 256, 0, stream>>>(labels, t.p, t.p_sorted, t.hist, B, C, row0, rows, k,

@@ -143,6 +143,30 @@ def test_sharded_loss_equals_global_loss():
     assert abs(float(full_loss) - float(ref)) < 1e-6 * abs(float(ref))
 
 
+def test_loss_across_sort_segments_matches_closed_form():
+    """Global batches above 4096 mentions span several sort segments; shards need not be aligned to them.  Checked
+    against the oracle's closed form (exact integer counts -> tight tolerance), with exact ties and all-zero label rows."""
+    from drin_b200.loss import triplet_loss_sharded
+    g = torch.Generator().manual_seed(9)
+    B, Cn = 5000, 11
+    s = torch.rand(B, Cn, generator=g) * 2 - 1
+    s[:, 1] = s[:, 0]
+    ans = torch.randint(0, Cn, (B,), generator=g)
+    y = torch.cat([torch.eye(Cn - 1, dtype=torch.uint8), torch.zeros(1, Cn - 1, dtype=torch.uint8)])[ans]
+    sd, yd = s.cuda(), y.cuda()
+    shares, parts = [], []
+    for row0, rows in ((0, 3000), (3000, 1500), (4500, 500)):          # the middle shard straddles segments 0 and 1
+        l, d = triplet_loss_sharded(sd, yd, 0.25, row0, rows)
+        want_l, want_d = O.triplet_sharded(s, y, 0.25, row0, rows)
+        assert abs(float(l) - float(want_l)) <= 1e-6 * abs(float(want_l))
+        assert rel_err(d.cpu(), want_d) < 1e-6
+        shares.append(float(l))
+        parts.append(d.clone())
+    full_l, full_d = triplet_loss_sharded(sd, yd, 0.25)
+    assert torch.equal(torch.cat(parts), full_d)
+    assert abs(sum(shares) - float(full_l)) < 1e-6 * abs(float(full_l))
+
+
 def test_fused_adam_matches_torch_adam():
     torch.manual_seed(0)
     model = drin_b200.Model().cuda()
