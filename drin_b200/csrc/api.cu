@@ -120,6 +120,7 @@ int drin_debug_option(const char* name, int32_t value) {
   else if (!strcmp(name, "score_fwd_variant")) debug_set_score_fwd_variant(value);
   else if (!strcmp(name, "layer_fwd_variant")) debug_set_layer_fwd_variant(value);
   else if (!strcmp(name, "layer_bwd_variant")) debug_set_layer_bwd_variant(value);
+  else if (!strcmp(name, "defer_reductions")) debug_set_defer_reductions(value);
   else return fail(DRIN_ERR_ARG, "drin_debug_option: unknown option '%s'", name);
   return DRIN_OK;
 }

@@ -102,11 +102,14 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
     ws.dfu_p = m.planes(2 * B * D, split);
     ws.dedges = m.take<float>(2 * 4 * BC);           // ping-pong between layers
     ws.dx0 = m.planes(rows * D, split);
-    // split-K: enough slices to fill the machine for the [D, D] weight gradients (18 tiles each)
+    // split-K: enough slices to fill the machine for the [D, D] weight gradients (18 tiles each).  Every
+    // weight-gradient GEMM of a pass owns a region of the arena, so that all reductions can run in ONE launch at the end.
     ws.ksplit = 8;
-    ws.partial = m.take<float>((size_t)ws.ksplit * D * D > (size_t)3 * D * R ? (size_t)ws.ksplit * D * D : (size_t)3 * D * R);
+    ws.partial_floats = (size_t)(3 * L + 2) * ws.ksplit * D * D + (size_t)2 * 3 * D * R;
+    ws.partial = m.take<float>(ws.partial_floats);
     ws.colsum_ctas = backward_ctas();
-    ws.colsum = m.take<float>((size_t)2 * ws.colsum_ctas * 3 * D);
+    ws.colsum_floats = (size_t)(3 * L + 2) * ws.colsum_ctas * 3 * D;     // same idea for the column-sum partials
+    ws.colsum = m.take<float>(ws.colsum_floats);
   }
   ws.bytes = align_up(m.off, 256);
   return DRIN_OK;

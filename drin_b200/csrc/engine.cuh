@@ -46,8 +46,10 @@ struct Workspace {
   Planes dfu_p;
   float* dedges = nullptr;           // [4, BC] gradient w.r.t. the edges entering the layer above
   Planes dx0;                        // [2B+2BC, D] gradient w.r.t. projection outputs (A of projection dW GEMMs)
-  float* partial = nullptr;          // split-K partial sums
-  float* colsum = nullptr;           // per-CTA partial column sums (bias / LayerNorm gradients)
+  float* partial = nullptr;          // split-K partial-sum arena: one region per weight-gradient GEMM of the pass
+  size_t partial_floats = 0;
+  float* colsum = nullptr;           // per-CTA partial column sums (bias / LayerNorm gradients): one region per producer
+  size_t colsum_floats = 0;
   int colsum_ctas = 0;
   int ksplit = 1;
 };

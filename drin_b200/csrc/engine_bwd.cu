@@ -16,9 +16,35 @@ static Operand op(const Planes& p, long long rows, int cols, long long row_offse
   return o;
 }
 
+// Deferred reductions of one backward pass: split-K slices and per-CTA column sums are written to private regions
+// of two arenas and reduced by two launches at the very end (instead of 8 + 5 small launches in between).
+static int g_defer_reductions = 1;       // test / A-B hook: 0 runs every reduction right after its producer
+void debug_set_defer_reductions(int v) { g_defer_reductions = v < 0 ? 1 : v; }
+
+struct Deferred {
+  SplitKJobs splitk;
+  ColsumJobs colsum;
+  cudaStream_t stream;
+  int D;
+  // column sums: queue (default) or reduce immediately
+  int add_colsum(const float* src0, int ctas0, const float* src1, int ctas1, int nvec, float* out0, float* out1, float* out2) {
+    if (!g_defer_reductions) return colsum_reduce(stream, src0, ctas0, src1, ctas1, nvec, D, out0, out1, out2);
+    return colsum.add(src0, ctas0, src1, ctas1, nvec, out0, out1, out2) ? fail(DRIN_ERR_ARG, "internal: too many column-sum jobs") : DRIN_OK;
+  }
+  float* partial_next;
+  float* partial_end;
+  float* colsum_next;
+  float* colsum_end;
+  float* take_colsum(size_t n) {
+    float* p = colsum_next;
+    colsum_next += n;
+    return colsum_next <= colsum_end ? p : nullptr;
+  }
+};
+
 // C[M,N] = A[K,M]^T B[K,N], contraction split so that tiles * slices ~ one wave
-static int weight_grad(cudaStream_t s, const Workspace& ws, const Operand& A, const Operand& B, int M, int N, long long K,
-                       float* out) {
+static int weight_grad(cudaStream_t s, const Workspace& ws, Deferred& df, const Operand& A, const Operand& B, int M, int N,
+                       long long K, float* out) {
   if (!out) return fail(DRIN_ERR_ARG, "gradient buffer is null");
   GemmEpilogue ep;
   ep.C = out;
@@ -27,7 +53,10 @@ static int weight_grad(cudaStream_t s, const Workspace& ws, const Operand& A, co
   int ksplit = 148 / tiles;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > ws.ksplit) ksplit = ws.ksplit;
-  return gemm_tcgen05(s, GEMM_TN, A, B, M, N, K, ep, ksplit, ws.partial);
+  float* region = df.partial_next;
+  df.partial_next += (size_t)ksplit * M * N;
+  if (df.partial_next > df.partial_end) return fail(DRIN_ERR_WORKSPACE, "internal: split-K arena exhausted");
+  return gemm_tcgen05(s, GEMM_TN, A, B, M, N, K, ep, ksplit, region, g_defer_reductions ? &df.splitk : nullptr);
 }
 
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,
@@ -41,8 +70,11 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
   if (ws.colsum_ctas != backward_ctas()) return fail(DRIN_ERR_ARG, "internal: partial-sum grid mismatch");
   const long long B = c.batch, C = c.candidates, BC = B * C;
   const int D = c.embed_dim, R = c.resnet_dim, L = c.gcn_layers;
-  float* partA = ws.colsum;
-  float* partB = ws.colsum + (size_t)ws.colsum_ctas * 3 * D;
+  Deferred df;
+  df.stream = stream; df.D = D;
+  df.partial_next = ws.partial; df.partial_end = ws.partial + ws.partial_floats;
+  df.colsum_next = ws.colsum; df.colsum_end = ws.colsum + ws.colsum_floats;
+  const size_t part_floats = (size_t)ws.colsum_ctas * 3 * D;
   float* dedges[2] = {ws.dedges, ws.dedges + 4 * BC};
 
   for (int l = L - 1; l >= 0; --l) {
@@ -53,16 +85,18 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       ScoreBwdArgs sa{};
       sa.B = c.batch; sa.C = c.candidates; sa.D = D;
       sa.h_mt = lw.h; sa.h_et = lw.h + B * D; sa.gamma = lp.ln_w; sa.beta = lp.ln_b; sa.dscores = dscores;
-      sa.dh_hi = ws.dh.hi; sa.dh_lo = ws.dh.lo; sa.partials = partA;
+      float* part = df.take_colsum(part_floats);
+      if (!part) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
+      sa.dh_hi = ws.dh.hi; sa.dh_lo = ws.dh.lo; sa.partials = part;
       DRIN_TRY(score_bwd(stream, sa));
-      DRIN_TRY(colsum_reduce(stream, partA, backward_ctas(), nullptr, 0, 3, D, lg.ln_w, lg.ln_b, lg.b_h));
+      DRIN_TRY(df.add_colsum(part, backward_ctas(), nullptr, 0, 3, lg.ln_w, lg.ln_b, lg.b_h));
     }
     // dZ = dH W_h ; dW_h = dH^T Z
     {
       GemmEpilogue ez;
       ez.C = ws.dz; ez.ldc = D;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dh, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, ez));
-      DRIN_TRY(weight_grad(stream, ws, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
     }
     LayerBwdArgs la{};
     la.B = c.batch; la.C = c.candidates; la.D = D; la.full = lw.full;
@@ -99,6 +133,10 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       la.dbeta = ws.dbeta;
     }
     la.dxm = ws.dxm;
+    float* partA = df.take_colsum(part_floats);
+    float* partB = df.take_colsum(part_floats);
+    float* partC = df.take_colsum(part_floats);
+    if (!partA || !partB || !partC) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
     la.partials = partA;
     DRIN_TRY(gcn_layer_bwd(stream, la));
 
@@ -107,10 +145,10 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       GemmEpilogue ef;
       ef.C = ws.dfu; ef.ldc = D;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.dg_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, ef));
-      DRIN_TRY(dfu_finish(stream, D, ws.dfu, ws.dbeta, lp.b_v, lw.fu, 2 * B, ws.dfu_p.hi, ws.dfu_p.lo, partB));
-      DRIN_TRY(colsum_reduce(stream, partB, backward_ctas(), nullptr, 0, 2, D, lg.b_u, lg.b_v, nullptr));
-      DRIN_TRY(weight_grad(stream, ws, op(lw.fu_p, 2 * B, D), op(ws.dg_p, 2 * B, D), D, D, 2 * B, lg.w_v));
-      DRIN_TRY(weight_grad(stream, ws, op(ws.dfu_p, 2 * B, D), op(lw.xm_p, 2 * B, D), D, D, 2 * B, lg.w_u));
+      DRIN_TRY(dfu_finish(stream, D, ws.dfu, ws.dbeta, lp.b_v, lw.fu, 2 * B, ws.dfu_p.hi, ws.dfu_p.lo, partC));
+      DRIN_TRY(df.add_colsum(partC, backward_ctas(), nullptr, 0, 2, lg.b_u, lg.b_v, nullptr));
+      DRIN_TRY(weight_grad(stream, ws, df, op(lw.fu_p, 2 * B, D), op(ws.dg_p, 2 * B, D), D, D, 2 * B, lg.w_v));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfu_p, 2 * B, D), op(lw.xm_p, 2 * B, D), D, D, 2 * B, lg.w_u));
       GemmEpilogue ex;
       ex.C = ws.dxu; ex.ldc = D;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dfu_p, 2 * B, D), op(lw.w_u, D, D), 2 * B, D, D, ex));
@@ -131,18 +169,21 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     DRIN_TRY(mention_bwd_finish(stream, ma));
     if (l > 0) {
       const drin_layer_params& pg = grads.layer[l - 1];
-      DRIN_TRY(colsum_reduce(stream, partA, layer_bwd_ctas(), partB, backward_ctas(), 3, D, pg.ln_w, pg.ln_b, pg.b_h));
+      DRIN_TRY(df.add_colsum(partA, layer_bwd_ctas(), partB, backward_ctas(), 3, pg.ln_w, pg.ln_b, pg.b_h));
     } else {
-      DRIN_TRY(colsum_reduce(stream, partA, layer_bwd_ctas(), nullptr, 0, 3, D, grads.b_et, grads.b_ei, nullptr));
-      DRIN_TRY(colsum_reduce(stream, partB, backward_ctas(), nullptr, 0, 3, D, grads.b_mt, grads.b_mi, nullptr));
+      DRIN_TRY(df.add_colsum(partA, layer_bwd_ctas(), nullptr, 0, 3, grads.b_et, grads.b_ei, nullptr));
+      DRIN_TRY(df.add_colsum(partB, backward_ctas(), nullptr, 0, 3, grads.b_mt, grads.b_mi, nullptr));
     }
   }
 
   // input projections: dW = dX0^T A (no data gradient: the cached features are constants)
-  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, B, D, 0), op(ws.span, B, D), D, D, B, grads.w_mt));
-  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, B, D, B), op(ws.mim, B, R), D, R, B, grads.w_mi));
-  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, BC, D, 2 * B), op(ws.epool, BC, D), D, D, BC, grads.w_et));
-  DRIN_TRY(weight_grad(stream, ws, op(ws.dx0, BC, D, 2 * B + BC), op(ws.eimg, BC, R), D, R, BC, grads.w_ei));
+  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, B, D, 0), op(ws.span, B, D), D, D, B, grads.w_mt));
+  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, B, D, B), op(ws.mim, B, R), D, R, B, grads.w_mi));
+  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, BC, D, 2 * B), op(ws.epool, BC, D), D, D, BC, grads.w_et));
+  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, BC, D, 2 * B + BC), op(ws.eimg, BC, R), D, R, BC, grads.w_ei));
+  // every split-K slice and every per-CTA column partial of the pass is reduced here, in two launches
+  DRIN_TRY(splitk_reduce_multi(stream, df.splitk));
+  DRIN_TRY(colsum_reduce_multi(stream, df.colsum, D));
   return DRIN_OK;
 }
 

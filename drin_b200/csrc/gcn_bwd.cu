@@ -1175,6 +1175,39 @@ int colsum_reduce(cudaStream_t stream, const float* src0, int ctas0, const float
   return DRIN_OK;
 }
 
+// every deferred column-sum reduction of a backward pass in one launch: blockIdx.y selects the job
+__global__ void __launch_bounds__(256) colsum_reduce_multi_kernel(const ColsumJobs jobs, int D) {
+  __shared__ float red[8][33];
+  const ColsumJob j = jobs.job[blockIdx.y];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;                  // flat (v, col)
+  float t = 0.f;
+  if (i < j.nvec * D) {
+    const int v = i / D, col = i - v * D;
+    for (int c = slice; c < j.ctas0; c += 8) t += j.src0[((long long)c * j.nvec + v) * D + col];
+    if (j.src1)
+      for (int c = slice; c < j.ctas1; c += 8) t += j.src1[((long long)c * j.nvec + v) * D + col];
+  }
+  red[slice][lane] = t;
+  __syncthreads();
+  if (slice == 0 && i < j.nvec * D) {
+    float r = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) r += red[s2][lane];
+    const int v = i / D, col = i - v * D;
+    float* out = v == 0 ? j.out0 : (v == 1 ? j.out1 : j.out2);
+    if (out) out[col] = r;
+  }
+}
+
+int colsum_reduce_multi(cudaStream_t stream, const ColsumJobs& jobs, int D) {
+  if (jobs.count <= 0) return DRIN_OK;
+  prof::Scope prof_scope(stream, prof::GCN_BWD);
+  colsum_reduce_multi_kernel<<<dim3((3 * D + 31) / 32, jobs.count), 256, 0, stream>>>(jobs, D);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
 int backward_ctas() { return BW_CTAS; }
 int layer_bwd_ctas() { return BS_GRID; }
 

@@ -32,10 +32,28 @@ struct GemmEpilogue {
   int ld_planes = 0;
 };
 
+// A split-K reduction that has not been run yet (see gemm_tcgen05 `defer`): C[M, ldc] = bias + sum_s partial[s]
+struct SplitKJob {
+  const float* partial;
+  long long split_stride;   // elements between slices
+  float* C;
+  const float* bias;
+  long long M;
+  int N, ldc, ksplit;
+};
+struct SplitKJobs {
+  static constexpr int MAX = 32;
+  SplitKJob job[MAX];
+  int count = 0;
+};
+// one launch that finishes every deferred split-K GEMM of a backward pass
+int splitk_reduce_multi(cudaStream_t stream, const SplitKJobs& jobs);
+
 // ksplit > 1: the contraction is cut into ksplit slices, slice s writes partial[s][M][ldc] (fp32, no
 // bias) and a second kernel reduces the slices deterministically into C (adding bias if given).
 int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M, int N,
-                 long long K, const GemmEpilogue& ep, int ksplit = 1, float* partial = nullptr);
+                 long long K, const GemmEpilogue& ep, int ksplit = 1, float* partial = nullptr,
+                 SplitKJobs* defer = nullptr);   // defer: append the reduction to the list instead of launching it
 
 // fp32 CUDA-core reference of the same contract (bring-up / unit tests only; never on the product path)
 int gemm_reference_simt(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M,

@@ -448,6 +448,33 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
   }
 }
 
+// all deferred split-K reductions of a backward pass in one launch: blockIdx.y selects the job
+__global__ void splitk_reduce_multi_kernel(const SplitKJobs jobs) {
+  const SplitKJob j = jobs.job[blockIdx.y];
+  const int n4 = j.N / 4;
+  const long long total4 = j.M * (long long)n4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n4;
+    const int c = (int)(i - r * n4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j.bias) acc = *reinterpret_cast<const float4*>(j.bias + c);
+    for (int s = 0; s < j.ksplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(j.partial + s * j.split_stride + r * j.ldc + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(j.C + r * j.ldc + c) = acc;
+  }
+}
+
+int splitk_reduce_multi(cudaStream_t stream, const SplitKJobs& jobs) {
+  if (jobs.count <= 0) return DRIN_OK;
+  prof::Scope prof_scope(stream, prof::GEMM);
+  splitk_reduce_multi_kernel<<<dim3(148, jobs.count), 256, 0, stream>>>(jobs);
+  DRIN_LAUNCH_CHECK();
+  return DRIN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
@@ -570,7 +597,7 @@ static int gemm_init_once() {
 }
 
 int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M, int N,
-                 long long K, const GemmEpilogue& ep, int ksplit, float* partial) {
+                 long long K, const GemmEpilogue& ep, int ksplit, float* partial, SplitKJobs* defer) {
   prof::Scope prof_scope(stream, prof::GEMM, 2.0 * (double)M * (double)N * (double)K, 0);
   DRIN_TRY(gemm_init_once());
   if (M <= 0 || N <= 0 || K <= 0) return fail(DRIN_ERR_ARG, "gemm: empty problem M=%lld N=%d K=%lld", M, N, K);
@@ -648,7 +675,10 @@ int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const
   }
   DRIN_CUDA(le);
   DRIN_LAUNCH_CHECK();
-  if (ksplit > 1) {
+  if (ksplit > 1 && defer) {
+    if (defer->count >= SplitKJobs::MAX) return fail(DRIN_ERR_ARG, "gemm: too many deferred split-K reductions");
+    defer->job[defer->count++] = SplitKJob{partial, p.c_split_stride, ep.C, ep.bias, M, N, ep.ldc, ksplit};
+  } else if (ksplit > 1) {
     const long long total4 = M * (long long)(N / 4);
     const int rgrid = (int)((total4 + 255) / 256 < 4 * g_num_sms ? (total4 + 255) / 256 : 4 * g_num_sms);
     splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(partial, ksplit, p.c_split_stride, ep.C, M, N, ep.ldc, ep.bias);

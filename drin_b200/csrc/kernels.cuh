@@ -97,6 +97,7 @@ void debug_set_score_bwd_variant(int v);
 void debug_set_score_fwd_variant(int v);
 void debug_set_layer_fwd_variant(int v);
 void debug_set_layer_bwd_variant(int v);
+void debug_set_defer_reductions(int v);
 
 struct LayerBwdArgs {
   int B, C, D;
@@ -132,6 +133,23 @@ int dfu_finish(cudaStream_t stream, int D, float* dfu, const float* dbeta, const
                long long rows, bf16* out_hi, bf16* out_lo, float* partials);
 int colsum_reduce(cudaStream_t stream, const float* src0, int ctas0, const float* src1, int ctas1, int nvec, int D,
                   float* out0, float* out1, float* out2);
+// deferred column-sum reductions (same contract as colsum_reduce), all run by ONE launch at the end of backward
+struct ColsumJob {
+  const float* src0; const float* src1;
+  int ctas0, ctas1, nvec;
+  float* out0; float* out1; float* out2;
+};
+struct ColsumJobs {
+  static constexpr int MAX = 4 * DRIN_MAX_LAYERS + 4;
+  ColsumJob job[MAX];
+  int count = 0;
+  int add(const float* src0, int ctas0, const float* src1, int ctas1, int nvec, float* out0, float* out1, float* out2) {
+    if (count >= MAX) return 1;
+    job[count++] = ColsumJob{src0, src1, ctas0, ctas1, nvec, out0, out1, out2};
+    return 0;
+  }
+};
+int colsum_reduce_multi(cudaStream_t stream, const ColsumJobs& jobs, int D);
 int backward_ctas();      // grid of score_bwd / mention_bwd_finish / dfu_finish (rows of their partial buffers)
 int layer_bwd_ctas();     // grid of gcn_layer_bwd
 
