@@ -54,6 +54,14 @@ int drin_backward(const drin_config* cfg, const drin_inputs* in, const drin_para
   return backward(*cfg, *in, *params, workspace, workspace_bytes, dscores, *grads, (cudaStream_t)stream);
 }
 
+int drin_backward_ex(const drin_config* cfg, const drin_inputs* in, const drin_params* params, void* workspace,
+                     size_t workspace_bytes, const float* dscores, const drin_params* grads, void* layers_done_event,
+                     void* stream) {
+  if (!cfg || !in || !params || !grads) return fail(DRIN_ERR_ARG, "drin_backward_ex: null argument");
+  return backward(*cfg, *in, *params, workspace, workspace_bytes, dscores, *grads, (cudaStream_t)stream,
+                  (cudaEvent_t)layers_done_event);
+}
+
 int drin_loss_scratch_bytes(int32_t batch_global, int32_t candidates, size_t* bytes) {
   if (!bytes || batch_global <= 0) return fail(DRIN_ERR_ARG, "drin_loss_scratch_bytes: bad argument");
   *bytes = triplet_scratch_bytes(batch_global, candidates);

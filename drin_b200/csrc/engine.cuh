@@ -61,6 +61,7 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
 int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace, size_t workspace_bytes,
             float* scores, cudaStream_t stream);
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,
-             size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream);
+             size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream,
+             cudaEvent_t layers_done = nullptr);
 
 }  // namespace drin

@@ -60,7 +60,8 @@ static int weight_grad(cudaStream_t s, const Workspace& ws, Deferred& df, const 
 }
 
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,
-             size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream) {
+             size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream,
+             cudaEvent_t layers_done) {
   if (!c.training) return fail(DRIN_ERR_ARG, "drin_backward needs a config with training = 1");
   Workspace ws;
   DRIN_TRY(plan_workspace(c, &in, workspace, ws));
@@ -174,6 +175,15 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       DRIN_TRY(df.add_colsum(partA, layer_bwd_ctas(), nullptr, 0, 3, grads.b_et, grads.b_ei, nullptr));
       DRIN_TRY(df.add_colsum(partB, backward_ctas(), nullptr, 0, 3, grads.b_mt, grads.b_mi, nullptr));
     }
+  }
+
+  if (layers_done) {
+    // a data-parallel caller wants to start reducing the layer gradients now: finish them (two launches) and signal
+    DRIN_TRY(splitk_reduce_multi(stream, df.splitk));
+    DRIN_TRY(colsum_reduce_multi(stream, df.colsum, D));
+    df.splitk.count = 0;
+    df.colsum.count = 0;
+    DRIN_CUDA(cudaEventRecord(layers_done, stream));
   }
 
   // input projections: dW = dX0^T A (no data gradient: the cached features are constants)

@@ -266,7 +266,10 @@ class Engine:
                                              C.c_size_t(ws.numel()), _ptr(scores), _stream()), "drin_forward")
         return scores, (pb, cfg, ws)
 
-    def backward(self, ctx, batch, params, dscores: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+    def backward(self, ctx, batch, params, dscores: torch.Tensor, grads: Dict[str, torch.Tensor],
+                 layers_done: Optional[torch.cuda.Event] = None) -> None:
+        """layers_done: optional event recorded on the current stream once every GCN-layer and bias gradient is final
+        (only the four input-projection weight gradients still follow)."""
         pb, cfg, ws = ctx
         if ws is not self._ws:
             raise RuntimeError("workspace was re-planned between forward and backward")
@@ -275,8 +278,9 @@ class Engine:
             ins = self.inputs(batch)
             ps = self.params(params, pb.D, pb.R)
             gs = self.params(grads, pb.D, pb.R)
-            _lib.check(self.lib.drin_backward(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
-                                              C.c_size_t(ws.numel()), _ptr(dscores), C.byref(gs), _stream()),
+            ev = C.c_void_p(0 if layers_done is None else layers_done.cuda_event)
+            _lib.check(self.lib.drin_backward_ex(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
+                                                 C.c_size_t(ws.numel()), _ptr(dscores), C.byref(gs), ev, _stream()),
                        "drin_backward")
 
     def debug_buffer(self, ctx, name: str, layer: int = 0) -> torch.Tensor:

@@ -190,6 +190,10 @@ class Model(nn.Module):
     def _param_views(self) -> Dict[str, torch.Tensor]:
         return {k: self._flat[o:o + n].view(shape) for k, (o, n, shape) in self._offsets.items()}
 
+    def layer_grad_offset(self) -> int:
+        """Offset in the flat buffers where the GCN-layer parameters start (the vertex-encoder tensors come first)."""
+        return self._offsets["gcn_layers.0.w_h.weight"][0]
+
     def dead_mask(self) -> torch.Tensor:
         """uint8 mask over the flat buffer: 1 where the reference never produces a gradient."""
         m = torch.zeros(self._flat.numel(), dtype=torch.uint8, device=self._flat.device)

@@ -117,6 +117,14 @@ int drin_forward(const drin_config* cfg, const drin_inputs* in, const drin_param
 int drin_backward(const drin_config* cfg, const drin_inputs* in, const drin_params* params, void* workspace,
                   size_t workspace_bytes, const float* dscores, const drin_params* grads, void* stream);
 
+/* Same as drin_backward; additionally records `layers_done_event` (a cudaEvent_t passed as void*, may be NULL) on
+ * `stream` at the point where every gradient of the GCN layers and every bias gradient is final and only the four
+ * input-projection weight gradients (w_mt, w_mi, w_et, w_ei) are still to come.  A data-parallel caller can start
+ * all-reducing the layer gradients on another stream while those GEMMs run. */
+int drin_backward_ex(const drin_config* cfg, const drin_inputs* in, const drin_params* params, void* workspace,
+                     size_t workspace_bytes, const float* dscores, const drin_params* grads, void* layers_done_event,
+                     void* stream);
+
 /* TripletLoss (common/utils.py:35-43) forward and backward in one call, for the rows
  * [row_offset, row_offset + rows_local) of a global score matrix (data-parallel: scores of all ranks are
  * gathered first, because the loss couples every mention with every score of the batch).
