@@ -26,44 +26,6 @@ namespace drin {
 // ---------------------------------------------------------------------------------------------
 // gcn_layer_fwd
 // ---------------------------------------------------------------------------------------------
-// process one candidate vertex row: returns nothing, updates the per-warp message slices in smem,
-// writes z = x + message as planes and returns the two edge-update dot products (FULL).
-template <int D, bool FULL>
-__device__ __forceinline__ void layer_fwd_row(const float* __restrict__ xrow, bool ln, const float* s_gamma,
-                                              const float* s_beta, const float* s_mt, const float* s_mi,
-                                              const float* s_gmt, const float* s_gmi, float e_mt, float e_mi,
-                                              float* acc_mt, float* acc_mi, bool write_z, bf16* z_hi, bf16* z_lo,
-                                              int lane, float& dot_mt, float& dot_mi) {
-  RowT<D> x;
-  row_load<D>(x, xrow, lane);
-  if (ln) row_ln_gelu<D>(x, s_gamma, s_beta, lane);
-  if (FULL) {
-    dot_mt = row_dot<D>(x, s_gmt, lane);
-    dot_mi = row_dot<D>(x, s_gmi, lane);
-  }
-#pragma unroll
-  for (int j = 0; j < RowT<D>::NV; ++j) {
-    const int off = (j * 32 + lane) * 4;
-    float4 am = *reinterpret_cast<float4*>(acc_mt + off);
-    am.x += e_mt * x.v[4 * j]; am.y += e_mt * x.v[4 * j + 1]; am.z += e_mt * x.v[4 * j + 2]; am.w += e_mt * x.v[4 * j + 3];
-    *reinterpret_cast<float4*>(acc_mt + off) = am;
-    if (FULL) {
-      float4 ai = *reinterpret_cast<float4*>(acc_mi + off);
-      ai.x += e_mi * x.v[4 * j]; ai.y += e_mi * x.v[4 * j + 1]; ai.z += e_mi * x.v[4 * j + 2]; ai.w += e_mi * x.v[4 * j + 3];
-      *reinterpret_cast<float4*>(acc_mi + off) = ai;
-    }
-    if (write_z) {
-      const float4 mt = *reinterpret_cast<const float4*>(s_mt + off);
-      const float4 mi = *reinterpret_cast<const float4*>(s_mi + off);
-      x.v[4 * j] += e_mt * mt.x + e_mi * mi.x;
-      x.v[4 * j + 1] += e_mt * mt.y + e_mi * mi.y;
-      x.v[4 * j + 2] += e_mt * mt.z + e_mi * mi.z;
-      x.v[4 * j + 3] += e_mt * mt.w + e_mi * mi.w;
-    }
-  }
-  if (write_z) row_store_planes<D>(x, z_hi, z_lo, lane);
-}
-
 // Shared-memory staged version: a producer warp streams each mention's candidate rows (and its four
 // mention-side vectors) into a 2-stage ring with 1-D bulk async copies (TMA engine, mbarrier completion);
 // NW consumer warps process rows out of shared memory.  Bytes in flight are set by the ring (up to ~78 KB
@@ -403,15 +365,14 @@ static int launch_layer_fwd_warp(cudaStream_t stream, const LayerFwdArgs& a) {
   return DRIN_OK;
 }
 
-static int g_layer_fwd_variant = -1;     // -1 auto, 0 staged CTA-per-mention, 1 warp-per-mention x 8, 2 x 12 (test hook)
+static int g_layer_fwd_variant = -1;     // -1 auto, 0 staged CTA-per-mention, >= 1 warp-per-mention (test hook)
 void debug_set_layer_fwd_variant(int v) { g_layer_fwd_variant = v; }
 
 int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: gcn_embed_dim %d not built (768 only)", a.D);
   const int variant = g_layer_fwd_variant < 0 ? (a.B >= 148 * 8 ? 1 : 0) : g_layer_fwd_variant;
-  if (variant == 1) return launch_layer_fwd_warp<768, 8>(stream, a);
-  if (variant == 2) return launch_layer_fwd_warp<768, 12>(stream, a);
+  if (variant >= 1) return launch_layer_fwd_warp<768, 8>(stream, a);     // 12 warps / SM measured slower (spills, tail)
   return launch_layer_fwd<768, 8>(stream, a);
 }
 
