@@ -62,6 +62,13 @@ def load():
                     raise RuntimeError(f"libdrin_b200.so is missing and could not be built: {e}") from e
         lib = C.CDLL(path)
         lib.drin_last_error.restype = C.c_char_p
+        # the ctypes mirrors above must match the structs the library was compiled with
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        lib.drin_struct_sizes(C.byref(a), C.byref(b), C.byref(c))
+        want = (C.sizeof(DrinConfig), C.sizeof(DrinInputs), C.sizeof(DrinParams))
+        if (a.value, b.value, c.value) != want:
+            raise RuntimeError(f"libdrin_b200.so ABI mismatch: struct sizes {(a.value, b.value, c.value)} != {want} "
+                               "(stale library? rebuild with python -m drin_b200.build --force)")
         _lib = lib
         return lib
 

@@ -10,7 +10,12 @@ using namespace drin;
 extern "C" {
 
 const char* drin_last_error(void) { return drin::last_error(); }
-int drin_version(void) { return 100; }
+int drin_version(void) { return 101; }
+void drin_struct_sizes(int32_t* config_bytes, int32_t* inputs_bytes, int32_t* params_bytes) {
+  if (config_bytes) *config_bytes = (int32_t)sizeof(drin_config);
+  if (inputs_bytes) *inputs_bytes = (int32_t)sizeof(drin_inputs);
+  if (params_bytes) *params_bytes = (int32_t)sizeof(drin_params);
+}
 
 int drin_split_planes(const float* x, void* hi, void* lo, int64_t n, void* stream) {
   return split_planes((cudaStream_t)stream, x, (bf16*)hi, (bf16*)lo, n);

@@ -100,6 +100,8 @@ typedef struct drin_params {
 
 const char* drin_last_error(void);
 int drin_version(void);
+/* sizeof(drin_config), sizeof(drin_inputs), sizeof(drin_params) as compiled: lets a binding check its struct mirrors */
+void drin_struct_sizes(int32_t* config_bytes, int32_t* inputs_bytes, int32_t* params_bytes);
 
 /* Bytes of caller-owned scratch drin_forward / drin_backward need for `cfg` (activations saved for the
  * backward pass live here when cfg->training != 0). */
