@@ -60,6 +60,8 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
     if (in) ws.eimg.hi = const_cast<bf16*>(static_cast<const bf16*>(in->entity_image_feature));
   }
   ws.edges0 = m.take<float>(4 * BC);
+  ws.slices = row_kernel_slices(c.batch, c.candidates);
+  if (ws.slices > 1) ws.acc_part = m.take<float>(B * ws.slices * 2 * D);
   ws.x0 = m.take<float>((2 * B + 2 * BC) * D);
   ws.xm0_p = m.planes(2 * B * D, split);
   for (int l = 0; l < L; ++l) {
@@ -239,6 +241,8 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
     }
     la.z_hi = lw.z.hi;
     la.z_lo = lw.z.lo;
+    la.slices = ws.slices;
+    la.acc_part = ws.acc_part;
     DRIN_TRY(gcn_layer_fwd(stream, la));
     GemmEpilogue eh;
     eh.ldc = D; eh.C = lw.h; eh.bias = lp.b_h;

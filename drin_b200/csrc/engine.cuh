@@ -31,6 +31,8 @@ struct Workspace {
   Planes w_mt, w_et, w_mi, w_ei;
   Planes span, mim, epool, eimg;     // projection A operands
   float* edges0 = nullptr;           // [4, BC]
+  int slices = 1;                    // candidate slices per mention of the row kernels (row_kernel_slices)
+  float* acc_part = nullptr;         // [B * slices][2][D] partial messages of sliced mentions (slices > 1)
   float* x0 = nullptr;               // [2B+2BC, D] projection outputs (mt, mi, et, ei)
   Planes xm0_p;                      // planes of the first 2B rows of x0
   LayerWs layer[DRIN_MAX_LAYERS];

@@ -235,11 +235,24 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_fwd_warp_kernel(const La
   const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
   const float en0 = a.en[0], en1 = a.en[1], en2 = a.en[2], en3 = a.en[3];
   const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
+  const int S = a.slices, cps = (a.C + S - 1) / S;            // work unit = (mention, candidate slice)
+  const long long units = B * S;
 
-  for (long long b = gwarp; b < B; b += nwarps) {
+  for (long long u = gwarp; u < units; u += nwarps) {
+    const long long b = u / S;
+    const int c0 = (int)(u - b * S) * cps, c1 = min(a.C, c0 + cps);
+    if (c0 >= a.C) {                                          // empty trailing slice (C not a multiple of the slice size)
+      float* part = a.acc_part + u * 2 * D;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        *reinterpret_cast<float4*>(part + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(part + D + (j * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
     RowT<D> pet, pei;                                         // prefetched rows of the next candidate
-    row_load<D>(pet, a.x_et + b * a.C * D, lane);
-    row_load<D>(pei, a.x_ei + b * a.C * D, lane);
+    row_load<D>(pet, a.x_et + (b * a.C + c0) * D, lane);
+    row_load<D>(pei, a.x_ei + (b * a.C + c0) * D, lane);
     {
       RowT<D> t;
       row_load<D>(t, a.xm + b * D, lane);
@@ -258,19 +271,26 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_fwd_warp_kernel(const La
     float acc_mt[NE], acc_mi[NE];
 #pragma unroll
     for (int i = 0; i < NE; ++i) acc_mt[i] = acc_mi[i] = 0.f;
-    long long r = b * a.C;
+    long long r = b * a.C + c0;
     float n0 = a.edges_in[r], n1 = a.edges_in[BC + r], n2 = a.edges_in[2 * BC + r], n3 = a.edges_in[3 * BC + r];
-    for (int c = 0; c < a.C; ++c, ++r) {
+    for (int c = c0; c < c1; ++c, ++r) {
       RowT<D> xet = pet, xei = pei;
       // enable mask (model.py:122); edge order tt (mt-et), ti (mt-ei), it (mi-et), ii (mi-ei)
       const float e0 = n0 * en0, e1 = n1 * en1, e2 = n2 * en2, e3 = n3 * en3;
-      if (c + 1 < a.C) {
+      if (c + 1 < c1) {
         row_load<D>(pet, a.x_et + (r + 1) * D, lane);
         row_load<D>(pei, a.x_ei + (r + 1) * D, lane);
         n0 = a.edges_in[r + 1]; n1 = a.edges_in[BC + r + 1]; n2 = a.edges_in[2 * BC + r + 1]; n3 = a.edges_in[3 * BC + r + 1];
       }
       if (lane == 0) {        // DRAM latency runs two candidates ahead of the register loads (bulk L2 prefetch)
-        const long long pr = c + 2 < a.C ? r + 2 : (b + nwarps < B ? (b + nwarps) * a.C + (c + 2 - a.C) : -1);
+        long long pr = -1;
+        if (c + 2 < c1) {
+          pr = r + 2;
+        } else if (u + nwarps < units) {                      // first rows of this warp's next unit
+          const long long nb = (u + nwarps) / S;
+          const int nc0 = (int)(u + nwarps - nb * S) * cps;
+          pr = nb * a.C + min(nc0 + (c + 2 - c1), a.C - 1);
+        }
         if (pr >= 0) {
           l2_prefetch(a.x_et + pr * D, D * 4);
           l2_prefetch(a.x_ei + pr * D, D * 4);
@@ -315,6 +335,19 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_fwd_warp_kernel(const La
         }
       }
     }
+    if (S > 1) {
+      // sliced mention: leave the partial messages to layer_fwd_mention_finish (fixed slice order -> deterministic)
+      float* part = a.acc_part + u * 2 * D;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int off = (j * 32 + lane) * 4;
+        *reinterpret_cast<float4*>(part + off) = make_float4(acc_mt[4 * j], acc_mt[4 * j + 1], acc_mt[4 * j + 2], acc_mt[4 * j + 3]);
+        if (FULL)
+          *reinterpret_cast<float4*>(part + D + off) = make_float4(acc_mi[4 * j], acc_mi[4 * j + 1], acc_mi[4 * j + 2], acc_mi[4 * j + 3]);
+      }
+      __syncwarp();
+      continue;
+    }
     // mention rows: z_m = x_m + mean over ALL C slots of the messages
     RowT<D> zm;
     row_load<D>(zm, v_mt, lane);
@@ -328,6 +361,35 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_fwd_warp_kernel(const La
       row_store_planes<D>(zm, a.z_hi + (B + b) * D, a.z_lo ? a.z_lo + (B + b) * D : nullptr, lane);
     }
     __syncwarp();                                             // the vector slice is rewritten for the next mention
+  }
+}
+
+// sliced mentions: z_m = x_m + (sum over slices of the partial messages) / C, one warp per mention row
+template <int D>
+__global__ void __launch_bounds__(256) layer_fwd_mention_finish_kernel(const LayerFwdArgs a) {
+  constexpr int NE = RowT<D>::NV * 4;
+  const int lane = threadIdx.x & 31;
+  const long long B = a.B;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = a.full ? 2 * B : B;                  // mt rows, then mi rows
+  const float invC = 1.0f / (float)a.C;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const long long b = r < B ? r : r - B;
+    const int which = r < B ? 0 : 1;
+    RowT<D> z, t;
+    row_load<D>(z, a.xm + r * D, lane);
+    RowT<D> acc;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) acc.v[i] = 0.f;
+    for (int sl = 0; sl < a.slices; ++sl) {
+      row_load<D>(t, a.acc_part + ((b * a.slices + sl) * 2 + which) * D, lane);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) acc.v[i] += t.v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) z.v[i] = z.v[i] + acc.v[i] * invC;
+    row_store_planes<D>(z, a.z_hi + r * D, a.z_lo ? a.z_lo + r * D : nullptr, lane);
   }
 }
 
@@ -362,7 +424,28 @@ static int launch_layer_fwd_warp(cudaStream_t stream, const LayerFwdArgs& a) {
     gcn_layer_fwd_warp_kernel<D, NW, false><<<148, NW * 32, smem, stream>>>(a);
   }
   DRIN_LAUNCH_CHECK();
+  if (a.slices > 1) {
+    const long long rows = a.full ? 2LL * a.B : a.B;
+    const int grid = (int)((rows + 7) / 8 < 148 * 4 ? (rows + 7) / 8 : 148 * 4);
+    layer_fwd_mention_finish_kernel<D><<<grid, 256, 0, stream>>>(a);
+    DRIN_LAUNCH_CHECK();
+  }
   return DRIN_OK;
+}
+
+int row_kernel_slices(int B, int C) {
+  const int max_slices = C / 8;                       // at least 8 candidates per slice
+  if (max_slices < 2) return 1;
+  const long long warps = 148LL * 8;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_slices; ++s) {
+    const long long units = (long long)B * s;
+    const long long rounds = (units + warps - 1) / warps;
+    const double eff = (double)units / (double)(rounds * warps);
+    if (eff > best_eff + 1e-9) { best = s; best_eff = eff; }     // ties: fewer slices (less per-slice overhead)
+  }
+  return best;
 }
 
 static int g_layer_fwd_variant = -1;     // -1 auto, 0 staged CTA-per-mention, >= 1 warp-per-mention (test hook)
@@ -371,8 +454,14 @@ void debug_set_layer_fwd_variant(int v) { g_layer_fwd_variant = v; }
 int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_FWD);
   if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: gcn_embed_dim %d not built (768 only)", a.D);
-  const int variant = g_layer_fwd_variant < 0 ? (a.B >= 148 * 8 ? 1 : 0) : g_layer_fwd_variant;
-  if (variant >= 1) return launch_layer_fwd_warp<768, 8>(stream, a);     // 12 warps / SM measured slower (spills, tail)
+  const int slices = a.slices > 0 ? a.slices : 1;
+  const int variant = g_layer_fwd_variant < 0 ? ((long long)a.B * slices >= 148 * 8 ? 1 : 0) : g_layer_fwd_variant;
+  if (variant >= 1) {                                        // 12 warps / SM measured slower (spills, tail)
+    if (slices > 1 && !a.acc_part) return fail(DRIN_ERR_ARG, "gcn_layer_fwd: sliced launch without a partial buffer");
+    LayerFwdArgs b = a;
+    b.slices = slices;
+    return launch_layer_fwd_warp<768, 8>(stream, b);
+  }
   return launch_layer_fwd<768, 8>(stream, a);
 }
 
@@ -493,7 +582,7 @@ __global__ void __launch_bounds__(NW * 32) score_kernel(const float* __restrict_
 template <int D, int NW>
 __global__ void __launch_bounds__(NW * 32, 2) score_warp_kernel(const float* __restrict__ h_mt, const float* __restrict__ h_et,
                                                               const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int B, int C,
+                                                              const float* __restrict__ beta, int B, int C, int S,
                                                               float* __restrict__ scores) {
   constexpr int NE = RowT<D>::NV * 4;
   __shared__ __align__(16) float s_gamma[D];
@@ -505,21 +594,32 @@ __global__ void __launch_bounds__(NW * 32, 2) score_warp_kernel(const float* __r
   }
   __syncthreads();
   const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
-  for (long long b = gwarp; b < B; b += nwarps) {
+  const int cps = (C + S - 1) / S;                            // work unit = (mention, candidate slice)
+  const long long units = (long long)B * S;
+  for (long long u = gwarp; u < units; u += nwarps) {
+    const long long b = u / S;
+    const int c0 = (int)(u - b * S) * cps, c1 = min(C, c0 + cps);
+    if (c0 >= C) continue;                                    // empty trailing slice
     RowT<D> m, hn;
     row_load<D>(m, h_mt + b * D, lane);
-    row_load<D>(hn, h_et + b * C * D, lane);
+    row_load<D>(hn, h_et + (b * C + c0) * D, lane);
     row_ln_gelu<D>(m, s_gamma, s_beta, lane);
     float qm = 0.f;
 #pragma unroll
     for (int i = 0; i < NE; ++i) qm = fmaf(m.v[i], m.v[i], qm);
     const float nm = fmaxf(sqrtf(warp_sum(qm)), 1e-8f);
-    for (int c = 0; c < C; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const long long r = b * C + c;
       RowT<D> e = hn;
-      if (c + 1 < C) row_load<D>(hn, h_et + (r + 1) * D, lane);
+      if (c + 1 < c1) row_load<D>(hn, h_et + (r + 1) * D, lane);
       if (lane == 0) {
-        const long long pr = c + 3 < C ? r + 3 : (b + nwarps < B ? (b + nwarps) * C + min(c + 3 - C, C - 1) : -1);
+        long long pr = -1;
+        if (c + 3 < c1) {
+          pr = r + 3;
+        } else if (u + nwarps < units) {
+          const long long nb = (u + nwarps) / S;
+          pr = nb * C + min((int)(u + nwarps - nb * S) * cps + (c + 3 - c1), C - 1);
+        }
         if (pr >= 0) l2_prefetch(h_et + pr * D, D * 4);
       }
       row_ln_gelu<D>(e, s_gamma, s_beta, lane);
@@ -544,9 +644,10 @@ int score_fwd(cudaStream_t stream, int D, const float* h_mt, const float* h_et, 
   prof::Scope prof_scope(stream, prof::SCORE);
   if (D != 768) return fail(DRIN_ERR_ARG, "score: gcn_embed_dim %d not built (768 only)", D);
   constexpr int WNW = 8, WGRID = 148 * 2;     // 2 CTAs / SM (<= 128 registers)
-  const bool warp_kernel = g_score_fwd_variant < 0 ? B >= WGRID * WNW : g_score_fwd_variant >= 1;
+  const int S = row_kernel_slices(B, C);
+  const bool warp_kernel = g_score_fwd_variant < 0 ? (long long)B * S >= 148 * 8 : g_score_fwd_variant >= 1;
   if (warp_kernel) {
-    score_warp_kernel<768, WNW><<<WGRID, WNW * 32, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, scores);
+    score_warp_kernel<768, WNW><<<WGRID, WNW * 32, 0, stream>>>(h_mt, h_et, gamma, beta, B, C, S, scores);
     DRIN_LAUNCH_CHECK();
     return DRIN_OK;
   }

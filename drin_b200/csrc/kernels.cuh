@@ -74,8 +74,14 @@ struct LayerFwdArgs {
   float* edges_out;              // [4, BC]                   (full)
   bf16* z_hi;                    // [2B+2BC, D] (full: mt, mi, et, ei) or [B+BC, D] (last: mt, et)
   bf16* z_lo;                    // null in bf16 mode
+  int slices;                    // candidate slices per mention of the warp-per-(mention, slice) kernel (>= 1)
+  float* acc_part;               // [B * slices][2][D] partial messages to the mention vertices (slices > 1)
 };
 int gcn_layer_fwd(cudaStream_t stream, const LayerFwdArgs& a);
+// Work decomposition of the warp-autonomous row kernels: one warp per (mention, candidate slice).  1 for short
+// candidate lists (WikiDiverse); for long ones (WikiMEL, C = 101) the number of slices that best fills whole rounds of
+// 148 x 8 warps, with at least 8 candidates per slice.
+int row_kernel_slices(int B, int C);
 int mention_ln(cudaStream_t stream, int D, const float* h, long long rows, const float* gamma, const float* beta,
                float* x, bf16* x_hi, bf16* x_lo);
 int rowdot(cudaStream_t stream, int D, const float* x, long long rows, const float* w, float* out);
