@@ -54,7 +54,10 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
-        if not _build.is_fresh():
+        override = os.environ.get("DRIN_B200_LIB")        # A/B testing of two builds on the same box
+        if override:
+            path = override
+        elif not _build.is_fresh():
             try:
                 _build.build()
             except Exception as e:  # no nvcc on the box: use the shipped .so if there is one

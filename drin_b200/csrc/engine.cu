@@ -104,13 +104,17 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
     ws.dfu_p = m.planes(2 * B * D, split);
     ws.dedges = m.take<float>(2 * 4 * BC);           // ping-pong between layers
     ws.dx0 = m.planes(rows * D, split);
+    if (ws.slices > 1) {
+      ws.slice_part = m.take<float>(B * ws.slices * 4 * D);      // also holds the [D + 32] slice records of score_bwd
+      ws.slice_dbeta = m.take<float>(B * ws.slices * 2);
+    }
     // split-K: enough slices to fill the machine for the [D, D] weight gradients (18 tiles each).  Every
     // weight-gradient GEMM of a pass owns a region of the arena, so that all reductions can run in ONE launch at the end.
     ws.ksplit = 8;
     ws.partial_floats = (size_t)(3 * L + 2) * ws.ksplit * D * D + (size_t)2 * 3 * D * R;
     ws.partial = m.take<float>(ws.partial_floats);
     ws.colsum_ctas = backward_ctas();
-    ws.colsum_floats = (size_t)(3 * L + 2) * ws.colsum_ctas * 3 * D;     // same idea for the column-sum partials
+    ws.colsum_floats = (size_t)(3 * L + 3) * ws.colsum_ctas * 3 * D;     // same idea for the column-sum partials
     ws.colsum = m.take<float>(ws.colsum_floats);
   }
   ws.bytes = align_up(m.off, 256);

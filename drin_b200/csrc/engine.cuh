@@ -48,6 +48,8 @@ struct Workspace {
   Planes dfu_p;
   float* dedges = nullptr;           // [4, BC] gradient w.r.t. the edges entering the layer above
   Planes dx0;                        // [2B+2BC, D] gradient w.r.t. projection outputs (A of projection dW GEMMs)
+  float* slice_part = nullptr;       // [B * slices][4][D] per-slice sums of the sliced backward row kernels (slices > 1)
+  float* slice_dbeta = nullptr;      // [B * slices][2]
   float* partial = nullptr;          // split-K partial-sum arena: one region per weight-gradient GEMM of the pass
   size_t partial_floats = 0;
   float* colsum = nullptr;           // per-CTA partial column sums (bias / LayerNorm gradients): one region per producer

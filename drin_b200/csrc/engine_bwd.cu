@@ -89,8 +89,15 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
       float* part = df.take_colsum(part_floats);
       if (!part) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
       sa.dh_hi = ws.dh.hi; sa.dh_lo = ws.dh.lo; sa.partials = part;
-      DRIN_TRY(score_bwd(stream, sa));
-      DRIN_TRY(df.add_colsum(part, backward_ctas(), nullptr, 0, 3, lg.ln_w, lg.ln_b, lg.b_h));
+      float* part2 = nullptr;
+      if (ws.slices > 1) {
+        part2 = df.take_colsum(part_floats);
+        if (!part2) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
+      }
+      sa.slices = ws.slices; sa.slice_part = ws.slice_part; sa.partials2 = part2;
+      bool used2 = false;
+      DRIN_TRY(score_bwd(stream, sa, &used2));
+      DRIN_TRY(df.add_colsum(part, backward_ctas(), used2 ? part2 : nullptr, used2 ? backward_ctas() : 0, 3, lg.ln_w, lg.ln_b, lg.b_h));
     }
     // dZ = dH W_h ; dW_h = dH^T Z
     {
@@ -139,6 +146,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     float* partC = df.take_colsum(part_floats);
     if (!partA || !partB || !partC) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
     la.partials = partA;
+    la.slices = ws.slices; la.slice_part = ws.slice_part; la.slice_dbeta = ws.slice_dbeta;
     DRIN_TRY(gcn_layer_bwd(stream, la));
 
     if (lw.dyn) {

@@ -208,13 +208,22 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
   };
 
   const long long gwarp = (long long)blockIdx.x * NW + warp, nwarps = (long long)gridDim.x * NW;
-  for (long long b = gwarp; b < B; b += nwarps) {
+  const int S = a.slices, cps = (a.C + S - 1) / S;        // work unit = (mention, candidate slice)
+  const long long units = B * S;
+  for (long long u = gwarp; u < units; u += nwarps) {
+    const long long b = u / S;
+    const int c0 = (int)(u - b * S) * cps, c1 = min(a.C, c0 + cps);
+    if (c0 >= a.C) {                                      // empty trailing slice
+      float* part = a.slice_part + u * (D + 32);
+      for (int i = lane; i < D + 32; i += 32) part[i] = 0.f;
+      continue;
+    }
     // ---- mention row: activated vertex -> smem (read back as float4 by the candidate rows), norm
     RowT<D> xm, actm, dactm;
     row_load<D>(xm, a.h_mt + b * D, lane);
     RowT<D> hn;                                           // prefetched candidate row
-    row_load<D>(hn, a.h_et + b * a.C * D, lane);
-    float ds_n = a.dscores[b * a.C];
+    row_load<D>(hn, a.h_et + (b * a.C + c0) * D, lane);
+    float ds_n = a.dscores[b * a.C + c0];
     const float rstd_m = row_ln_gelu_recompute<D>(xm, actm, dactm, s_gamma, s_beta, lane);   // xm := xhat
     float qm = 0.f;
 #pragma unroll
@@ -229,16 +238,22 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
 #pragma unroll
     for (int i = 0; i < NE; ++i) dam.v[i] = 0.f;
     float coef = 0.f;
-    for (int c = 0; c < a.C; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const long long r = b * a.C + c;
       RowT<D> h = hn, e, de;
       const float ds = ds_n;
-      if (c + 1 < a.C) {
+      if (c + 1 < c1) {
         row_load<D>(hn, a.h_et + (r + 1) * D, lane);
         ds_n = a.dscores[r + 1];
       }
       if (lane == 0) {        // DRAM latency runs ahead of the register prefetch (bulk L2 prefetch)
-        const long long pr = c + 3 < a.C ? r + 3 : (b + nwarps < B ? (b + nwarps) * a.C + min(c + 3 - a.C, a.C - 1) : -1);
+        long long pr = -1;
+        if (c + 3 < c1) {
+          pr = r + 3;
+        } else if (u + nwarps < units) {
+          const long long nb = (u + nwarps) / S;
+          pr = nb * a.C + min((int)(u + nwarps - nb * S) * cps + (c + 3 - c1), a.C - 1);
+        }
         if (pr >= 0) l2_prefetch(a.h_et + pr * D, D * 4);
       }
       asm volatile("" ::: "memory");                         // keeps the prefetch and the row's math apart (registers)
@@ -276,6 +291,14 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
       asm volatile("" ::: "memory");
       const long long zr = B + r;
       row_store_planes<D>(e, a.dh_hi + zr * D, a.dh_lo ? a.dh_lo + zr * D : nullptr, lane);
+    }
+    if (S > 1) {
+      // sliced mention: leave the slice's share of dL/da_m to score_bwd_mention_finish (fixed slice order)
+      float* part = a.slice_part + u * (D + 32);
+      row_store<D>(dam, part, lane);
+      if (lane == 0) part[D] = coef;
+      __syncwarp();
+      continue;
     }
     // ---- mention row gradient: dL/da_m = sum_c w1_c a_e_c - (sum_c ds_c cs_c / nm^2) a_m
     {
@@ -315,22 +338,76 @@ __global__ void __launch_bounds__(NW * 32, 1) score_bwd_warp_kernel(const ScoreB
   }
 }
 
+// sliced mentions: dL/da_m = sum over slices of the partial sums - (sum of coefficients) * a_m, then through
+// LayerNorm + GELU of the mention row; column partials go to their own buffer (second source of the reduction)
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32) score_bwd_mention_finish_kernel(const ScoreBwdArgs a) {
+  constexpr int NE = RowT<D>::NV * 4;
+  extern __shared__ __align__(16) float sm[];
+  float* s_gamma = sm;
+  float* s_beta = s_gamma + D;
+  float* s_part = s_beta + D;              // [3][NW][D]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += NW * 32) {
+    s_gamma[i] = a.gamma[i];
+    s_beta[i] = a.beta[i];
+  }
+  for (int i = tid; i < 3 * NW * D; i += NW * 32) s_part[i] = 0.f;
+  __syncthreads();
+  float* pg = s_part + (0 * NW + warp) * D;
+  float* pb = s_part + (1 * NW + warp) * D;
+  float* ph = s_part + (2 * NW + warp) * D;
+  for (long long b = (long long)blockIdx.x * NW + warp; b < a.B; b += (long long)gridDim.x * NW) {
+    RowT<D> h, act, dact, d, t;
+    row_load<D>(h, a.h_mt + b * D, lane);
+    RowT<D> xhat = h;
+    const float rstd = row_ln_gelu_recompute<D>(xhat, act, dact, s_gamma, s_beta, lane);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) d.v[i] = 0.f;
+    float coef = 0.f;
+    for (int sl = 0; sl < a.slices; ++sl) {
+      const float* part = a.slice_part + (b * a.slices + sl) * (D + 32);
+      row_load<D>(t, part, lane);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) d.v[i] += t.v[i];
+      coef += part[D];
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) d.v[i] = fmaf(-coef, act.v[i], d.v[i]);
+    row_ln_gelu_bwd_from<D>(xhat, dact, rstd, d, s_gamma, pg, pb, lane);
+    row_accum_smem<D>(d, ph, lane);
+    row_store_planes<D>(d, a.dh_hi + b * D, a.dh_lo ? a.dh_lo + b * D : nullptr, lane);
+  }
+  __syncthreads();
+  flush_partials<D, NW>(s_part, 3, a.partials2, tid);
+}
+
 static int g_score_bwd_variant = -1;     // -1 auto, 0 CTA-per-mention kernel, 1 warp-autonomous kernel (test hook)
 void debug_set_score_bwd_variant(int v) { g_score_bwd_variant = v; }
 
-int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a) {
+int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a_in, bool* used_partials2) {
   prof::Scope prof_scope(stream, prof::SCORE);
+  ScoreBwdArgs a = a_in;
+  if (a.slices < 1 || !a.slice_part || !a.partials2) a.slices = 1;
+  if (used_partials2) *used_partials2 = false;
   if (a.D != 768) return fail(DRIN_ERR_ARG, "score_bwd: gcn_embed_dim %d not built (768 only)", a.D);
   constexpr int D = 768;
   constexpr int WNW = 8, WGRID = 148;
-  const bool warp_kernel = g_score_bwd_variant < 0 ? a.B >= WGRID * WNW : g_score_bwd_variant >= 1;
-  if (warp_kernel) {            // enough mentions for one per warp: barrier-free register-accumulating kernel
+  const bool warp_kernel = g_score_bwd_variant < 0 ? (long long)a.B * a.slices >= WGRID * WNW : g_score_bwd_variant >= 1;
+  if (warp_kernel) {            // enough (mention, slice) units for one per warp: barrier-free register-accumulating kernel
     const size_t smem = (size_t)(2 + WNW + 3 * WNW) * D * sizeof(float);
     DRIN_CUDA(cudaFuncSetAttribute(score_bwd_warp_kernel<D, WNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     score_bwd_warp_kernel<D, WNW><<<WGRID, WNW * 32, smem, stream>>>(a, BW_CTAS);
     DRIN_LAUNCH_CHECK();
+    if (a.slices > 1) {
+      const size_t fsmem = (size_t)(2 + 3 * BW_NW) * D * sizeof(float);
+      score_bwd_mention_finish_kernel<D, BW_NW><<<BW_CTAS, BW_NW * 32, fsmem, stream>>>(a);
+      DRIN_LAUNCH_CHECK();
+      if (used_partials2) *used_partials2 = true;
+    }
     return DRIN_OK;
   }
+  a.slices = 1;
   const size_t smem = (size_t)(3 + BW_NW + 3 * BW_NW) * D * sizeof(float);
   DRIN_CUDA(cudaFuncSetAttribute(score_bwd_kernel<D, BW_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_bwd_kernel<D, BW_NW><<<BW_CTAS, BW_NW * 32, smem, stream>>>(a);
@@ -670,7 +747,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) gcn_layer_bwd_stream_kernel(con
 // candidates (messages to the mention vertices, g gradients) live in a private shared-memory slice of the warp; the
 // kernel-long column sums (bias / LayerNorm parameter gradients) live in registers.  No CTA barrier in the row loop;
 // all sums run in candidate order and the per-warp partials are combined once, in a fixed order, at the end.
-template <int D, int NW, bool FULL, bool LN>
+template <int D, int NW, bool FULL, bool LN, bool SLICED>
 __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const LayerBwdArgs a, int partial_rows) {
   constexpr int NV = RowT<D>::NV, NE = NV * 4;
   constexpr int NVEC = FULL ? 6 : 3;             // xm_t, xm_i, dz_mt (, dz_mi, g_mt, g_mi)
@@ -732,13 +809,29 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
       l2_prefetch(a.g + (B + m) * D, ROW_BYTES);
     }
   };
-  if (lane == 0 && gwarp < B) {
-    prefetch_candidate(gwarp * a.C);
-    if (a.C > 1) prefetch_candidate(gwarp * a.C + 1);
+  // work unit = (mention, candidate slice); the unsliced instantiation (WikiDiverse-sized lists) folds S to 1
+  const int S = SLICED ? a.slices : 1, cps = (a.C + S - 1) / S;
+  const long long units = B * S;
+  auto unit_first_row = [&](long long u) {
+    const long long ub = u / S;
+    return ub * a.C + min((int)(u - ub * S) * cps, a.C - 1);
+  };
+  if (lane == 0 && gwarp < units) {
+    const long long fr = unit_first_row(gwarp);
+    prefetch_candidate(fr);
+    if (fr + 1 < BC) prefetch_candidate(fr + 1);
   }
 
-  for (long long b = gwarp; b < B; b += nwarps) {
-    const long long r0 = b * a.C;
+  for (long long u = gwarp; u < units; u += nwarps) {
+    const long long b = u / S;
+    const int c0 = (int)(u - b * S) * cps, nC = min(a.C, c0 + cps) - c0;     // candidates c0 .. c0 + nC - 1
+    if (SLICED && nC <= 0) {                     // empty trailing slice
+      float* part = a.slice_part + u * 4 * D;
+      for (int i = lane; i < 4 * D; i += 32) part[i] = 0.f;
+      if (lane < 2) a.slice_dbeta[u * 2 + lane] = 0.f;
+      continue;
+    }
+    const long long r0 = b * a.C + c0;
     RowT<D> ax, ad, bx, bd;                      // register sets of the et row pair and the ei row pair
     row_load<D>(ax, a.x_et + r0 * D, lane);
     if (!LATE_DZ) row_load<D>(ad, dz_et + r0 * D, lane);
@@ -902,7 +995,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
       row_store_planes<D>(d, a.dcand_hi + orow * D, a.dcand_lo ? a.dcand_lo + orow * D : nullptr, lane);
     };
 
-    for (int c = 0; c < a.C; ++c) {
+    for (int c = 0; c < nC; ++c) {
       const long long r = r0 + c;
       // per-candidate scalars (enable mask model.py:122; sigmoid backward of the dynamic edge update), loaded one
       // candidate ahead so their latency is off the critical path
@@ -915,7 +1008,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
         dbeta_mt += (ds[0] + ds[1]) * invD;
         dbeta_mi += (ds[2] + ds[3]) * invD;
       }
-      if (c + 1 < a.C) {
+      if (c + 1 < nC) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           ne[k] = a.edges_in[k * BC + r + 1];
@@ -925,27 +1018,44 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
           }
         }
       }
-      if (lane == 0) {        // L2 prefetch two candidates ahead (crossing into the warp's next mention)
-        if (c + 2 < a.C) {
+      if (lane == 0) {        // L2 prefetch two candidates ahead (crossing into the warp's next unit)
+        if (c + 2 < nC) {
           prefetch_candidate(r + 2);
-        } else if (b + nwarps < B) {
-          const long long nb = b + nwarps;
-          prefetch_candidate(nb * a.C + (c + 2 - a.C < a.C ? c + 2 - a.C : a.C - 1));
-          if (c + 2 == a.C) prefetch_mention(nb);
+        } else if (u + nwarps < units) {
+          const long long fr = unit_first_row(u + nwarps) + (c + 2 - nC);
+          prefetch_candidate(fr < BC ? fr : BC - 1);
+          if (c + 2 == nC) prefetch_mention((u + nwarps) / S);
         }
       }
       row_load<D>(bx, a.x_ei + r * D, lane);                    // ei rows arrive while the et row is processed
       if (FULL && !LATE_DZ) row_load<D>(bd, dz_ei + r * D, lane);
       process_row(std::integral_constant<int, 0>{}, r, ax, ad, dz_et + r * D, e[0], e[2], ds[0], ds[2]);
       asm volatile("" ::: "memory");                            // keep the two rows' instruction streams apart (registers)
-      if (c + 1 < a.C) {                                        // next candidate's et rows arrive during the ei row
+      if (c + 1 < nC) {                                         // next candidate's et rows arrive during the ei row
         row_load<D>(ax, a.x_et + (r + 1) * D, lane);
         if (!LATE_DZ) row_load<D>(ad, dz_et + (r + 1) * D, lane);
       }
       process_row(std::integral_constant<int, 1>{}, r, bx, bd, FULL ? dz_ei + r * D : nullptr, e[1], e[3], ds[1], ds[3]);
     }
-    // ---- mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
     __syncwarp();
+    if (SLICED) {
+      // sliced mention: the slice's sums go to layer_bwd_slice_finish (fixed slice order -> deterministic)
+      float* part = a.slice_part + u * 4 * D;
+      RowT<D> t;
+      row_load<D>(t, A_mt, lane); row_store<D>(t, part, lane);
+      row_load<D>(t, A_mi, lane); row_store<D>(t, part + D, lane);
+      if (dyn) {
+        row_load<D>(t, G_mt, lane); row_store<D>(t, part + 2 * D, lane);
+        row_load<D>(t, G_mi, lane); row_store<D>(t, part + 3 * D, lane);
+        if (lane == 0) {
+          a.slice_dbeta[u * 2] = dbeta_mt;
+          a.slice_dbeta[u * 2 + 1] = dbeta_mi;
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- mention-side results: dxm = dz_m + sum_c(...) ; dg ; dbeta
     {
       RowT<D> t, z;
       row_load<D>(t, A_mt, lane);
@@ -995,23 +1105,77 @@ __global__ void __launch_bounds__(NW * 32, 1) gcn_layer_bwd_warp_kernel(const La
   }
 }
 
+// sliced mentions: dxm = dz_m + sum over slices of A ; dg = sum of G ; dbeta = sum -- one warp per mention row
+template <int D>
+__global__ void __launch_bounds__(256) layer_bwd_slice_finish_kernel(const LayerBwdArgs a) {
+  constexpr int NE = RowT<D>::NV * 4;
+  const int lane = threadIdx.x & 31;
+  const long long B = a.B;
+  const bool dyn = a.full && a.g != nullptr;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < 2 * B; r += nwarps) {
+    const long long b = r < B ? r : r - B;
+    const int which = r < B ? 0 : 1;                     // mention text / mention image vertex
+    RowT<D> acc, t;
+    if (which == 0 || a.full) {
+      row_load<D>(acc, a.dz + r * D, lane);              // dz rows of this layer: mt rows, then (full) mi rows
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) acc.v[i] = 0.f;
+    }
+    for (int sl = 0; sl < a.slices; ++sl) {
+      row_load<D>(t, a.slice_part + ((b * a.slices + sl) * 4 + which) * D, lane);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) acc.v[i] += t.v[i];
+    }
+    row_store<D>(acc, a.dxm + r * D, lane);
+    if (dyn) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) acc.v[i] = 0.f;
+      float db = 0.f;
+      for (int sl = 0; sl < a.slices; ++sl) {
+        row_load<D>(t, a.slice_part + ((b * a.slices + sl) * 4 + 2 + which) * D, lane);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) acc.v[i] += t.v[i];
+        db += a.slice_dbeta[(b * a.slices + sl) * 2 + which];
+      }
+      row_store_planes<D>(acc, a.dg_hi + r * D, a.dg_lo ? a.dg_lo + r * D : nullptr, lane);
+      if (lane == 0) a.dbeta[r] = db;
+    }
+  }
+}
+
 static int g_layer_bwd_variant = -1;     // -1 auto, 0 staged CTA-per-SM kernel, 1 warp-per-mention kernel (test hook)
 void debug_set_layer_bwd_variant(int v) { g_layer_bwd_variant = v; }
 
 template <int D, int NW, bool FULL, bool LN>
 static int launch_layer_bwd_warp(cudaStream_t stream, const LayerBwdArgs& a) {
   const size_t smem = (size_t)(2 + NW * (FULL ? 10 : 5)) * D * sizeof(float);
-  DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_warp_kernel<D, NW, FULL, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gcn_layer_bwd_warp_kernel<D, NW, FULL, LN><<<BS_GRID, NW * 32, smem, stream>>>(a, BS_GRID);
+  if (a.slices > 1) {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_warp_kernel<D, NW, FULL, LN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcn_layer_bwd_warp_kernel<D, NW, FULL, LN, true><<<BS_GRID, NW * 32, smem, stream>>>(a, BS_GRID);
+  } else {
+    DRIN_CUDA(cudaFuncSetAttribute(gcn_layer_bwd_warp_kernel<D, NW, FULL, LN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcn_layer_bwd_warp_kernel<D, NW, FULL, LN, false><<<BS_GRID, NW * 32, smem, stream>>>(a, BS_GRID);
+  }
   DRIN_LAUNCH_CHECK();
+  if (a.slices > 1) {
+    const long long rows = 2LL * a.B;
+    const int grid = (int)((rows + 7) / 8 < 148 * 4 ? (rows + 7) / 8 : 148 * 4);
+    layer_bwd_slice_finish_kernel<D><<<grid, 256, 0, stream>>>(a);
+    DRIN_LAUNCH_CHECK();
+  }
   return DRIN_OK;
 }
 
-int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a) {
+int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a_in) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
-  if (a.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a.D);
+  if (a_in.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a_in.D);
   constexpr int D = 768;
-  const bool warp_kernel = g_layer_bwd_variant < 0 ? a.B >= BS_GRID * 7 : g_layer_bwd_variant >= 1;
+  LayerBwdArgs a = a_in;
+  if (a.slices < 1 || !a.slice_part || !a.slice_dbeta) a.slices = 1;
+  const bool warp_kernel = g_layer_bwd_variant < 0 ? (long long)a.B * a.slices >= BS_GRID * 7 : g_layer_bwd_variant >= 1;
   if (warp_kernel) {
     // 7 warps x 30 KB (full layers) or 8 warps x 15 KB (last layer) of private shared memory per SM
     const bool ln = a.ln_gamma != nullptr;

@@ -97,8 +97,13 @@ struct ScoreBwdArgs {
   const float* dscores;    // [B, C]
   bf16* dh_hi; bf16* dh_lo;   // [B+BC, D] (mt rows, then et rows)
   float* partials;         // [ctas][3][D]: dgamma, dbeta, db_h
+  // candidate slices (row_kernel_slices): with slices > 1 the mention rows are finished by a second kernel
+  int slices;
+  float* slice_part;       // [B * slices][D + 32]: partial dL/da_m of the slice, coefficient at [D]
+  float* partials2;        // [backward_ctas()][3][D]: column partials of the mention-finish kernel (slices > 1)
 };
-int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a);
+// returns via *used_partials2 whether partials2 was written (slices > 1 and the sliced kernel ran)
+int score_bwd(cudaStream_t stream, const ScoreBwdArgs& a, bool* used_partials2);
 void debug_set_score_bwd_variant(int v);
 void debug_set_score_fwd_variant(int v);
 void debug_set_layer_fwd_variant(int v);
@@ -122,6 +127,9 @@ struct LayerBwdArgs {
   bf16* dg_hi; bf16* dg_lo;   // [2B, D]   (full)
   float* dbeta;               // [2B]      (full)
   float* partials;            // [ctas][3][D]: ln -> (dgamma, dbeta, db_h) of the previous layer; else (db_et, db_ei, -)
+  int slices;                 // candidate slices (row_kernel_slices); > 1: mention-side results by a finish kernel
+  float* slice_part;          // [B * slices][4][D]: A_mt, A_mi, G_mt, G_mi partial sums of the slice
+  float* slice_dbeta;         // [B * slices][2]
 };
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a);
 
