@@ -23,6 +23,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "pipe.cuh"
+#include "rows.cuh"
 
 namespace drin {
 
@@ -349,48 +350,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const long long row_base = ((long long)m_blk * CTAS + cta_rank) * BM + q * 32;
       float* stg = reinterpret_cast<float*>(smem_raw + (stage_smem - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
       const int sub = lane >> 3, l8 = lane & 7;
-#pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + chunk * 32);
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + chunk * 32;
-        if (col0 >= p.N) continue;                       // warp-uniform
+      const long long rows_left = p.M - row_base;                     // rows of this warp that exist (may be <= 0)
+      const int rows_valid = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const int ncols = p.N - n_blk * BN;                             // columns of this tile that exist
+      const int nchunks = ncols >= BN ? BN / 32 : (ncols + 31) / 32;  // warp-uniform
+      // base pointers of the first row this thread stores (row sub, columns 4*l8 .. +3 of the chunk)
+      float* c_ptr = p.C ? p.C + (long long)ks * p.c_split_stride + (row_base + sub) * p.ldc + n_blk * BN + 4 * l8 : nullptr;
+      bf16* hi_ptr = p.out_hi ? p.out_hi + (row_base + sub) * p.ld_planes + n_blk * BN + 4 * l8 : nullptr;
+      bf16* lo_ptr = p.out_lo ? p.out_lo + (row_base + sub) * p.ld_planes + n_blk * BN + 4 * l8 : nullptr;
+
+      // one chunk = 32 accumulator columns: registers -> padded smem transpose -> 128-B row segments in global.
+      // The TMEM load of chunk i + 1 is issued before chunk i is stored, so its latency hides behind the stores;
+      // once the last load has landed the accumulator is handed back to the MMA warp.
+      auto store_chunk = [&](int chunk, const uint32_t (&v)[32]) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<uint4*>(stg + lane * EPI_LD + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         __syncwarp();
-        const int col = col0 + 4 * l8;
+        const int ccol = chunk * 32 + 4 * l8;                         // column inside the tile
+        const int col = n_blk * BN + ccol;
+        const bool full_cols = chunk * 32 + 32 <= ncols;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) {
-          if (col + 3 < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          if (full_cols || col + 3 < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           else {
             if (col < p.N) bv.x = __ldg(p.bias + col);
             if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
             if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
           }
         }
+        if (full_cols) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + sub;
-          const long long row = row_base + r;
-          float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * l8);
-          f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
-          if (row < p.M && col < p.N) {
-            if (col + 3 < p.N) {
-              if (p.C) *reinterpret_cast<float4*>(p.C + (long long)ks * p.c_split_stride + row * p.ldc + col) = f;
-              if (p.out_hi) {
-                bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-                split_bf16(f.x, h0, l0); split_bf16(f.y, h1, l1); split_bf16(f.z, h2, l2); split_bf16(f.w, h3, l3);
-                *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_planes + col) =
-                    make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-                if (p.out_lo)
-                  *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_planes + col) =
-                      make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + sub;
+            float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * l8);
+            f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+            if (r < rows_valid) {
+              if (c_ptr) *reinterpret_cast<float4*>(c_ptr + (long long)it * 4 * p.ldc + chunk * 32) = f;
+              if (hi_ptr) {
+                uint32_t h0, l0, h1, l1;
+                split_bf16x2(f.x, f.y, h0, l0);
+                split_bf16x2(f.z, f.w, h1, l1);
+                *reinterpret_cast<uint2*>(hi_ptr + (long long)it * 4 * p.ld_planes + chunk * 32) = make_uint2(h0, h1);
+                if (lo_ptr) *reinterpret_cast<uint2*>(lo_ptr + (long long)it * 4 * p.ld_planes + chunk * 32) = make_uint2(l0, l1);
               }
-            } else {
-              const float ff[4] = {f.x, f.y, f.z, f.w};
+            }
+          }
+        } else {                                                       // ragged last chunk of the tile (N % 32 != 0)
+#pragma unroll 1
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + sub;
+            const long long row = row_base + r;
+            float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * l8);
+            f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
+            const float ff[4] = {f.x, f.y, f.z, f.w};
+            if (r < rows_valid) {
               for (int j = 0; j < 4 && col + j < p.N; ++j) {
                 if (p.C) p.C[(long long)ks * p.c_split_stride + row * p.ldc + col + j] = ff[j];
                 if (p.out_hi) {
@@ -404,12 +419,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
         }
         __syncwarp();
+      };
+
+      uint32_t va[32], vb[32];
+      if (nchunks > 0) tmem_ld_32x32(taddr0, va);
+#pragma unroll 1
+      for (int chunk = 0; chunk < nchunks; chunk += 2) {
+        tmem_ld_wait();                                                // va = chunk
+        if (chunk + 1 < nchunks) tmem_ld_32x32(taddr0 + (uint32_t)((chunk + 1) * 32), vb);
+        else {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CTAS == 1) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_cluster(tempty_bar(acc), 0u);            // the leader's MMA thread waits for both CTAs
+          }
+        }
+        store_chunk(chunk, va);
+        if (chunk + 1 < nchunks) {
+          tmem_ld_wait();                                              // vb = chunk + 1
+          if (chunk + 2 < nchunks) tmem_ld_32x32(taddr0 + (uint32_t)((chunk + 2) * 32), va);
+          else {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CTAS == 1) mbar_arrive(tempty_bar(acc));
+              else mbar_arrive_cluster(tempty_bar(acc), 0u);
+            }
+          }
+          store_chunk(chunk + 1, vb);
+        }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 1) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(tempty_bar(acc), 0u);      // the leader's MMA thread waits for both CTAs
+      if (nchunks <= 0) {                                              // cannot happen (tiles start inside N); keep the protocol live
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 1) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(tempty_bar(acc), 0u);
+        }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
