@@ -65,3 +65,24 @@ def test_full_size_train_step_runs_and_loss_decreases():
     tr = drin_b200.Trainer(_model(cands + 1), lr=1e-3)
     losses = [float(tr.step(batch)) for _ in range(4)]
     assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def test_backward_with_layers_done_event_gives_identical_gradients():
+    """drin_backward_ex flushes the layer-gradient reductions early and records an event for a data-parallel caller;
+    the gradients are the same bits as with the plain call."""
+    B, cands = 64, 10
+    batch = make_batch("wikidiverse", B, 8, cands, device="cuda", generate_on_device=True)
+    m = _model(cands + 1)
+    eng, params = m._engine, m._param_views()
+    scores, ctx = eng.forward(tuple(batch[:-1]), params, training=True)
+    ds = torch.randn_like(scores)
+    plain = torch.zeros_like(m.flat_params)
+    eng.backward(ctx, tuple(batch[:-1]), params, ds, m._grad_views(plain))
+    ev = torch.cuda.Event()
+    ev.record()
+    torch.cuda.synchronize()
+    with_event = torch.zeros_like(m.flat_params)
+    eng.backward(ctx, tuple(batch[:-1]), params, ds, m._grad_views(with_event), layers_done=ev)
+    torch.cuda.synchronize()
+    assert ev.query()
+    assert torch.equal(plain, with_event)
