@@ -23,6 +23,7 @@ class DrinConfig(C.Structure):
         ("regions", c_int32), ("mention_objects", c_int32), ("entity_objects", c_int32), ("embed_dim", c_int32),
         ("resnet_dim", c_int32), ("gcn_layers", c_int32), ("precision", c_int32), ("training", c_int32),
         ("edge_enabled", c_float * 4), ("static_edges", c_int32), ("indexed", c_int32),
+        ("vector_edges", c_int32),
     ]
 
 
@@ -35,7 +36,7 @@ class DrinInputs(C.Structure):
 
 
 class DrinLayerParams(C.Structure):
-    _fields_ = [(n, c_void_p) for n in ("w_h", "b_h", "w_u", "b_u", "w_v", "b_v", "ln_w", "ln_b")]
+    _fields_ = [(n, c_void_p) for n in ("w_h", "b_h", "w_u", "b_u", "w_v", "b_v", "ln_w", "ln_b", "w_m", "b_m")]
 
 
 class DrinParams(C.Structure):

@@ -10,7 +10,7 @@ using namespace drin;
 extern "C" {
 
 const char* drin_last_error(void) { return drin::last_error(); }
-int drin_version(void) { return 101; }
+int drin_version(void) { return 102; }
 void drin_struct_sizes(int32_t* config_bytes, int32_t* inputs_bytes, int32_t* params_bytes) {
   if (config_bytes) *config_bytes = (int32_t)sizeof(drin_config);
   if (inputs_bytes) *inputs_bytes = (int32_t)sizeof(drin_inputs);
@@ -151,7 +151,10 @@ int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name,
   else if (!strcmp(name, "x0")) { *ptr = ws.x0; *rows = 2 * B + 2 * BC; *cols = D; }
   else if (!strcmp(name, "h")) { *ptr = lw.h; *rows = lw.rows; *cols = D; }
   else if (!strcmp(name, "xm")) { *ptr = lw.xm; *rows = 2 * B; *cols = D; }
-  else if (!strcmp(name, "fu")) { *ptr = lw.fu; *rows = 2 * B; *cols = D; }
+  else if (!strcmp(name, "fu")) { *ptr = lw.fu; *rows = 2 * B; *cols = ws.vec ? D / 2 : D; }
+  else if (!strcmp(name, "xa")) { *ptr = lw.xa; *rows = 2 * B + 2 * BC; *cols = D; }
+  else if (!strcmp(name, "fv")) { *ptr = lw.fv; *rows = 2 * BC; *cols = D / 2; }
+  else if (!strcmp(name, "q")) { *ptr = lw.q; *rows = 4 * BC; *cols = D; }
   else if (!strcmp(name, "g")) { *ptr = lw.g; *rows = 2 * B; *cols = D; }
   else if (!strcmp(name, "edges_out")) { *ptr = lw.edges_out; *rows = 4; *cols = BC; }
   else if (!strcmp(name, "dz")) { *ptr = ws.dz; *rows = 2 * B + 2 * BC; *cols = D; }

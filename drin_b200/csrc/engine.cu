@@ -35,6 +35,69 @@ struct Bump {
 };
 }  // namespace
 
+// Vector-edge layers (gcn_vec.cu): everything after x0.
+static int plan_vector(const drin_config& c, Bump& m, Workspace& ws) {
+  const bool split = c.precision == DRIN_FP32;
+  const size_t B = c.batch, C = c.candidates, D = c.embed_dim, R = c.resnet_dim, BC = B * C, H = D / 2;
+  const size_t rows_all = 2 * B + 2 * BC;
+  const int L = c.gcn_layers;
+  ws.x0_p = m.planes(rows_all * D, split);
+  ws.xm0_p = ws.x0_p;
+  for (int l = 0; l < L; ++l) {
+    LayerWs& lw = ws.layer[l];
+    lw.full = l < L - 1;
+    lw.dyn = lw.full;
+    lw.rows = lw.full ? (long long)rows_all : (long long)(B + BC);
+    lw.w_h = m.planes(D * D, split);
+    if (lw.dyn) {
+      lw.w_u = m.planes(H * D, split);
+      lw.w_v = m.planes(H * D, split);
+      lw.w_m = m.planes(D * D, split);
+    }
+    if (l == 0) {
+      lw.xa = ws.x0;
+      lw.xa_p = ws.x0_p;
+    } else {
+      lw.xa = m.take<float>(rows_all * D);
+      if (lw.dyn) lw.xa_p = m.planes(rows_all * D, split);
+    }
+    lw.xm = lw.xa;
+    if (lw.dyn) {
+      lw.fu = m.take<float>(2 * B * H);
+      lw.fv = m.take<float>(2 * BC * H);
+      lw.m_p = m.planes(4 * BC * D, split);
+      lw.q = m.take<float>(4 * BC * D);
+    }
+    lw.z = m.planes((size_t)lw.rows * D, split);
+    lw.h = m.take<float>((size_t)lw.rows * D);
+  }
+  if (c.training) {
+    ws.dh = m.planes(rows_all * D, split);
+    ws.dz = m.take<float>(rows_all * D);
+    ws.dxa = m.take<float>(rows_all * D);
+    ws.dxuv = m.take<float>(rows_all * D);
+    ws.dm = m.take<float>(4 * BC * D);
+    ws.dq_p = m.planes(4 * BC * D, split);
+    ws.dfu_p = m.planes(2 * B * H, split);
+    ws.dfv_p = m.planes(2 * BC * H, split);
+    ws.dx0 = m.planes(rows_all * D, split);
+    if (ws.slices > 1) {
+      ws.slice_part = m.take<float>(B * ws.slices * 4 * D);
+      ws.slice_dbeta = m.take<float>(B * ws.slices * 2);
+    }
+    ws.ksplit = 8;
+    ws.partial_floats = (size_t)(3 * L + 2) * ws.ksplit * D * D + (size_t)2 * 3 * D * R;
+    ws.partial = m.take<float>(ws.partial_floats);
+    ws.colsum_ctas = backward_ctas();
+    ws.colsum_floats = (size_t)2 * ws.colsum_ctas * 3 * D;        // score_bwd (and its sliced mention finish)
+    ws.colsum = m.take<float>(ws.colsum_floats);
+    ws.vec_part = m.take<float>((size_t)vec_layer_ctas() * 2 * D);
+    ws.rows_part = m.take<float>((size_t)vec_rows_ctas() * 4 * D);
+  }
+  ws.bytes = align_up(m.off, 256);
+  return DRIN_OK;
+}
+
 int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Workspace& ws) {
   DRIN_TRY(check_config(c));
   const bool split = c.precision == DRIN_FP32;
@@ -63,6 +126,8 @@ int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Work
   ws.slices = row_kernel_slices(c.batch, c.candidates);
   if (ws.slices > 1) ws.acc_part = m.take<float>(B * ws.slices * 2 * D);
   ws.x0 = m.take<float>((2 * B + 2 * BC) * D);
+  ws.vec = vector_path(c);
+  if (ws.vec) return plan_vector(c, m, ws);
   ws.xm0_p = m.planes(2 * B * D, split);
   for (int l = 0; l < L; ++l) {
     LayerWs& lw = ws.layer[l];
@@ -131,6 +196,54 @@ static Operand op(const Planes& p, long long rows, int cols, long long row_offse
   return o;
 }
 
+// GCN layers + scoring with vector edges (drin/model.py:205-209 with gcn_edge_feature == "vector").
+static int forward_vector_layers(const drin_config& c, const drin_params& p, Workspace& ws, float* scores,
+                                 cudaStream_t stream) {
+  const long long B = c.batch, C = c.candidates, BC = B * C;
+  const int D = c.embed_dim, H = D / 2, L = c.gcn_layers;
+  for (int l = 0; l < L; ++l) {
+    LayerWs& lw = ws.layer[l];
+    const drin_layer_params& lp = p.layer[l];
+    VecLayerArgs va{};
+    va.B = c.batch; va.C = c.candidates; va.D = D; va.full = lw.full; va.dyn = lw.dyn;
+    for (int k = 0; k < 4; ++k) va.en[k] = c.edge_enabled[k];
+    if (l == 0) {
+      va.e_scalar = ws.edges0;
+    } else {
+      const LayerWs& pw = ws.layer[l - 1];
+      const drin_layer_params& pp = p.layer[l - 1];
+      DRIN_TRY(mention_ln(stream, D, pw.h, 2 * B + 2 * BC, pp.ln_w, pp.ln_b, lw.xa, lw.dyn ? lw.xa_p.hi : nullptr,
+                          lw.dyn ? lw.xa_p.lo : nullptr));
+      va.q_in = pw.q;
+    }
+    va.xa = lw.xa;
+    if (lw.dyn) {
+      // model.py:149: fu = W_u u for the 2B mention vertices, fv = W_v v for the 2BC candidate vertices (D -> D/2)
+      GemmEpilogue ep;
+      ep.ldc = H;
+      ep.C = lw.fu; ep.bias = lp.b_u;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.xa_p, 2 * B, D), op(lw.w_u, H, D), 2 * B, H, D, ep));
+      ep.C = lw.fv; ep.bias = lp.b_v;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.xa_p, 2 * BC, D, 2 * B), op(lw.w_v, H, D), 2 * BC, H, D, ep));
+      va.fu = lw.fu; va.fv = lw.fv;
+      va.m_hi = lw.m_p.hi; va.m_lo = lw.m_p.lo;
+    }
+    va.z_hi = lw.z.hi; va.z_lo = lw.z.lo;
+    DRIN_TRY(vec_layer_fwd(stream, va));
+    GemmEpilogue eh;
+    eh.ldc = D; eh.C = lw.h; eh.bias = lp.b_h;
+    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.z, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, eh));
+    if (lw.dyn) {   // model.py:133: q = W_m(cat[fu, fv] + e) + b_m for the four edge types at once; sigmoid in the consumer
+      GemmEpilogue em;
+      em.ldc = D; em.C = lw.q; em.bias = lp.b_m;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.m_p, 4 * BC, D), op(lw.w_m, D, D), 4 * BC, D, D, em));
+    }
+  }
+  const LayerWs& last = ws.layer[L - 1];
+  return score_fwd(stream, D, last.h, last.h + B * D, p.layer[L - 1].ln_w, p.layer[L - 1].ln_b, c.batch, c.candidates,
+                   scores);
+}
+
 int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace, size_t workspace_bytes,
             float* scores, cudaStream_t stream) {
   Workspace ws;
@@ -153,8 +266,13 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
     for (int l = 0; l < L; ++l) {
       add(p.layer[l].w_h, ws.layer[l].w_h, (size_t)D * D);
       if (ws.layer[l].dyn) {
-        add(p.layer[l].w_u, ws.layer[l].w_u, (size_t)D * D);
-        add(p.layer[l].w_v, ws.layer[l].w_v, (size_t)D * D);
+        const size_t uv = ws.vec ? (size_t)(D / 2) * D : (size_t)D * D;
+        add(p.layer[l].w_u, ws.layer[l].w_u, uv);
+        add(p.layer[l].w_v, ws.layer[l].w_v, uv);
+        if (ws.vec) {
+          if (!p.layer[l].w_m || !p.layer[l].b_m) return fail(DRIN_ERR_ARG, "vector edges: layer %d has no w_m / b_m", l);
+          add(p.layer[l].w_m, ws.layer[l].w_m, (size_t)D * D);
+        }
       }
     }
     DRIN_TRY(split_planes_multi(stream, jobs));
@@ -195,11 +313,19 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
     ep.out_lo = ws.xm0_p.lo ? ws.xm0_p.lo + B * D : nullptr;
     DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.mim, B, R), op(ws.w_mi, D, R), B, D, R, ep));
     ep.out_hi = ep.out_lo = nullptr;
+    auto planes_at = [&](long long row) {          // vector edges: the candidate rows feed the W_v GEMM too
+      if (!ws.vec) return;
+      ep.out_hi = ws.x0_p.hi + row * D;
+      ep.out_lo = ws.x0_p.lo ? ws.x0_p.lo + row * D : nullptr;
+    };
     ep.C = ws.x0 + 2 * B * D; ep.bias = p.b_et;
+    planes_at(2 * B);
     DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.epool, BC, D), op(ws.w_et, D, D), BC, D, D, ep));
     ep.C = ws.x0 + (2 * B + BC) * D; ep.bias = p.b_ei;
+    planes_at(2 * B + BC);
     DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.eimg, BC, R), op(ws.w_ei, D, R), BC, D, R, ep));
   }
+  if (ws.vec) return forward_vector_layers(c, p, ws, scores, stream);
 
   // ---- GCN layers (model.py:205-206) ----
   for (int l = 0; l < L; ++l) {

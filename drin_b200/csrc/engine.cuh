@@ -24,6 +24,13 @@ struct LayerWs {
   Planes z;                    // [rows, D] A operand of the W_h GEMM
   float* h = nullptr;          // [rows, D] pre-LayerNorm output of W_h
   float* edges_out = nullptr;  // [4, BC] (full)
+  // ---- vector edges (gcn_edge_feature "vector" with a dynamic edge update; see gcn_vec.cu) ----
+  Planes w_m;                  // [D, D] planes (dyn); w_u / w_v are [D/2, D] here
+  float* xa = nullptr;         // [2B+2BC, D] activated vertices entering this layer (layer 0: alias of x0)
+  Planes xa_p;                 // planes of xa (dyn: A operand of the W_u / W_v GEMMs)
+  float* fv = nullptr;         // [2BC, D/2] W_v xv + b_v (dyn); fu above is [2B, D/2]
+  Planes m_p;                  // [4BC, D] cat[fu, fv] + E_k (dyn): A operand of the W_m GEMM
+  float* q = nullptr;          // [4BC, D] pre-sigmoid edge outputs W_m m + b_m (dyn)
 };
 
 struct Workspace {
@@ -56,7 +63,21 @@ struct Workspace {
   size_t colsum_floats = 0;
   int colsum_ctas = 0;
   int ksplit = 1;
+  // ---- vector edges ----
+  bool vec = false;                  // the vector-edge path runs (vector_edges && !static_edges && L > 1)
+  Planes x0_p;                       // planes of all rows of x0 (xm0_p aliases its first 2B rows)
+  float* dxa = nullptr;              // [2B+2BC, D] gradient w.r.t. the activated vertices (message paths)
+  float* dxuv = nullptr;             // [2B+2BC, D] W_u / W_v data gradients
+  float* dm = nullptr;               // [4BC, D] gradient w.r.t. m
+  Planes dq_p;                       // [4BC, D] gradient w.r.t. the pre-sigmoid edge outputs of the layer below
+  Planes dfv_p;                      // [2BC, D/2]; dfu_p above is [2B, D/2]
+  float* vec_part = nullptr;         // [vec_layer_ctas()][2][D] column partials of vec_layer_bwd
+  float* rows_part = nullptr;        // [vec_rows_ctas()][4][D] column partials of vec_rows_bwd
 };
+
+// vector edges with static edges (or one layer) never leave the scalar representation: model.py:135-136 passes the
+// masked, expanded input edges through, so the scalar kernels compute exactly the same thing.
+inline bool vector_path(const drin_config& c) { return c.vector_edges && !c.static_edges && c.gcn_layers > 1; }
 
 int check_config(const drin_config& c);
 // Carve `base` (may be null: size query) into the buffers above.

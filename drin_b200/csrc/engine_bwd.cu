@@ -59,6 +59,98 @@ static int weight_grad(cudaStream_t s, const Workspace& ws, Deferred& df, const 
   return gemm_tcgen05(s, GEMM_TN, A, B, M, N, K, ep, ksplit, region, g_defer_reductions ? &df.splitk : nullptr);
 }
 
+// Backward of the vector-edge layers (forward_vector_layers in engine.cu), layer by layer from the scores down:
+//   dZ = dH W_h, dW_h = dH^T Z;  [edge update] dM = dQ W_m, dW_m = dQ^T M;  vec_layer_bwd (messages, sigmoid, cat);
+//   [edge update] dW_u = dFu^T Xm, dW_v = dFv^T Xv, dX += dFu W_u | dFv W_v;  vec_rows_bwd (GELU + LayerNorm).
+static int backward_vector_layers(const drin_config& c, const drin_params& p, Workspace& ws, const float* dscores,
+                                  const drin_params& grads, Deferred& df, cudaStream_t stream) {
+  const long long B = c.batch, C = c.candidates, BC = B * C;
+  const int D = c.embed_dim, H = D / 2, L = c.gcn_layers;
+  const size_t part_floats = (size_t)ws.colsum_ctas * 3 * D;
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerWs& lw = ws.layer[l];
+    const drin_layer_params& lg = grads.layer[l];
+    if (l == L - 1) {
+      const drin_layer_params& lp = p.layer[l];
+      ScoreBwdArgs sa{};
+      sa.B = c.batch; sa.C = c.candidates; sa.D = D;
+      sa.h_mt = lw.h; sa.h_et = lw.h + B * D; sa.gamma = lp.ln_w; sa.beta = lp.ln_b; sa.dscores = dscores;
+      float* part = df.take_colsum(part_floats);
+      float* part2 = ws.slices > 1 ? df.take_colsum(part_floats) : nullptr;
+      if (!part || (ws.slices > 1 && !part2)) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
+      sa.dh_hi = ws.dh.hi; sa.dh_lo = ws.dh.lo; sa.partials = part;
+      sa.slices = ws.slices; sa.slice_part = ws.slice_part; sa.partials2 = part2;
+      bool used2 = false;
+      DRIN_TRY(score_bwd(stream, sa, &used2));
+      DRIN_TRY(df.add_colsum(part, backward_ctas(), used2 ? part2 : nullptr, used2 ? backward_ctas() : 0, 3, lg.ln_w, lg.ln_b, lg.b_h));
+    }
+    {
+      GemmEpilogue ez;
+      ez.C = ws.dz; ez.ldc = D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dh, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, ez));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
+    }
+    if (lw.dyn) {     // dq_p holds the gradient w.r.t. this layer's pre-sigmoid edge outputs (written by layer l + 1)
+      GemmEpilogue em;
+      em.C = ws.dm; em.ldc = D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dq_p, 4 * BC, D), op(lw.w_m, D, D), 4 * BC, D, D, em));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dq_p, 4 * BC, D), op(lw.m_p, 4 * BC, D), D, D, 4 * BC, lg.w_m));
+    }
+    VecLayerArgs va{};
+    va.B = c.batch; va.C = c.candidates; va.D = D; va.full = lw.full; va.dyn = lw.dyn;
+    for (int k = 0; k < 4; ++k) va.en[k] = c.edge_enabled[k];
+    va.xa = lw.xa;
+    if (l == 0) va.e_scalar = ws.edges0; else va.q_in = ws.layer[l - 1].q;
+    va.dz = ws.dz;
+    va.dxa = ws.dxa;
+    if (lw.dyn) {
+      va.dm = ws.dm;
+      va.dfu_hi = ws.dfu_p.hi; va.dfu_lo = ws.dfu_p.lo;
+      va.dfv_hi = ws.dfv_p.hi; va.dfv_lo = ws.dfv_p.lo;
+    }
+    if (l > 0) { va.dq_hi = ws.dq_p.hi; va.dq_lo = ws.dq_p.lo; }      // safe: dm / dW_m above already consumed dq_p
+    va.partials = ws.vec_part;
+    int prow = 0;
+    DRIN_TRY(vec_layer_bwd(stream, va, &prow));
+    if (l > 0) DRIN_TRY(strided_colsum(stream, ws.vec_part, prow, 2 * D, D, grads.layer[l - 1].b_m));
+    if (lw.dyn) {
+      DRIN_TRY(strided_colsum(stream, ws.vec_part + D, prow, 2 * D, H, lg.b_u));
+      DRIN_TRY(strided_colsum(stream, ws.vec_part + D + H, prow, 2 * D, H, lg.b_v));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfu_p, 2 * B, H), op(lw.xa_p, 2 * B, D), H, D, 2 * B, lg.w_u));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfv_p, 2 * BC, H), op(lw.xa_p, 2 * BC, D, 2 * B), H, D, 2 * BC, lg.w_v));
+      GemmEpilogue ex;
+      ex.C = ws.dxuv; ex.ldc = D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dfu_p, 2 * B, H), op(lw.w_u, H, D), 2 * B, D, H, ex));
+      ex.C = ws.dxuv + 2 * B * D;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dfv_p, 2 * BC, H), op(lw.w_v, H, D), 2 * BC, D, H, ex));
+    }
+    VecRowsBwdArgs ra{};
+    ra.B = B; ra.BC = BC; ra.D = D;
+    ra.d0 = ws.dxa;
+    ra.d1 = lw.dyn ? ws.dxuv : nullptr;
+    ra.partials = ws.rows_part;
+    const long long pstride = 4 * D;
+    if (l > 0) {
+      const drin_layer_params& pg = grads.layer[l - 1];
+      ra.h_prev = ws.layer[l - 1].h;
+      ra.ln_gamma = p.layer[l - 1].ln_w; ra.ln_beta = p.layer[l - 1].ln_b;
+      ra.out_hi = ws.dh.hi; ra.out_lo = ws.dh.lo;
+      DRIN_TRY(vec_rows_bwd(stream, ra));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part, vec_rows_ctas(), pstride, D, pg.ln_w));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part + D, vec_rows_ctas(), pstride, D, pg.ln_b));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part + 2 * D, vec_rows_ctas(), pstride, D, pg.b_h));
+    } else {
+      ra.out_hi = ws.dx0.hi; ra.out_lo = ws.dx0.lo;
+      DRIN_TRY(vec_rows_bwd(stream, ra));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part, vec_rows_ctas(), pstride, D, grads.b_mt));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part + D, vec_rows_ctas(), pstride, D, grads.b_mi));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part + 2 * D, vec_rows_ctas(), pstride, D, grads.b_et));
+      DRIN_TRY(strided_colsum(stream, ws.rows_part + 3 * D, vec_rows_ctas(), pstride, D, grads.b_ei));
+    }
+  }
+  return DRIN_OK;
+}
+
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,
              size_t workspace_bytes, const float* dscores, const drin_params& grads, cudaStream_t stream,
              cudaEvent_t layers_done) {
@@ -78,7 +170,8 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
   const size_t part_floats = (size_t)ws.colsum_ctas * 3 * D;
   float* dedges[2] = {ws.dedges, ws.dedges + 4 * BC};
 
-  for (int l = L - 1; l >= 0; --l) {
+  if (ws.vec) DRIN_TRY(backward_vector_layers(c, p, ws, dscores, grads, df, stream));
+  for (int l = ws.vec ? -1 : L - 1; l >= 0; --l) {
     const LayerWs& lw = ws.layer[l];
     const drin_layer_params& lp = p.layer[l];
     const drin_layer_params& lg = grads.layer[l];

@@ -42,7 +42,7 @@ struct SplitKJob {
   int N, ldc, ksplit;
 };
 struct SplitKJobs {
-  static constexpr int MAX = 32;
+  static constexpr int MAX = 40;
   SplitKJob job[MAX];
   int count = 0;
 };

@@ -31,7 +31,7 @@ struct SplitJob {
   long long n4;    // number of float4 (element count / 4)
 };
 struct SplitJobs {
-  static constexpr int MAX = 4 + 3 * DRIN_MAX_LAYERS;
+  static constexpr int MAX = 4 + 4 * DRIN_MAX_LAYERS;
   SplitJob job[MAX];
   int count = 0;
 };
@@ -166,6 +166,46 @@ struct ColsumJobs {
 int colsum_reduce_multi(cudaStream_t stream, const ColsumJobs& jobs, int D);
 int backward_ctas();      // grid of score_bwd / mention_bwd_finish / dfu_finish (rows of their partial buffers)
 int layer_bwd_ctas();     // grid of gcn_layer_bwd
+
+// gcn_vec.cu -- GCN layer with vector edges (gcn_edge_feature == "vector", drin/model.py:97-153)
+struct VecLayerArgs {
+  int B, C, D;
+  bool full;                  // all four vertex types are updated (every layer but the last)
+  bool dyn;                   // this layer runs the dynamic edge update (full layers of a dynamic-edge model)
+  float en[4];                // gcn_edge_enabled (model.py:122)
+  const float* xa;            // [2B+2BC, D] activated vertices entering the layer (mt, mi, et, ei)
+  const float* e_scalar;      // [4, BC] scalar input edges (first layer), or null:
+  const float* q_in;          // [4BC, D] PRE-sigmoid vector edges produced by the previous layer
+  // forward
+  const float* fu;            // [2B, D/2]  W_u xm + b_u   (dyn)
+  const float* fv;            // [2BC, D/2] W_v xv + b_v   (dyn; et rows, then ei rows)
+  bf16* z_hi; bf16* z_lo;     // [2B+2BC, D] (full) or [B+BC, D] (last: mt, et): A operand of the W_h GEMM
+  bf16* m_hi; bf16* m_lo;     // [4BC, D] cat[fu, fv] + E_k: A operand of the W_m GEMM (dyn)
+  // backward
+  const float* dz;            // gradient w.r.t. z, same row layout
+  const float* dm;            // [4BC, D] gradient w.r.t. m (dyn)
+  float* dxa;                 // [2B+2BC, D] gradient w.r.t. xa (message paths only; W_u / W_v paths are GEMMs)
+  bf16* dfu_hi; bf16* dfu_lo; // [2B, D/2]  (dyn)
+  bf16* dfv_hi; bf16* dfv_lo; // [2BC, D/2] (dyn)
+  bf16* dq_hi; bf16* dq_lo;   // [4BC, D] gradient w.r.t. q_in (vector edges in)
+  float* partials;            // [ctas][2][D]: sum dq (b_m gradient of the previous layer); [b_u | b_v] gradient
+};
+int vec_layer_fwd(cudaStream_t stream, const VecLayerArgs& a);
+int vec_layer_bwd(cudaStream_t stream, const VecLayerArgs& a, int* partial_rows);
+int vec_layer_ctas();
+struct VecRowsBwdArgs {
+  long long B, BC;
+  int D;
+  const float* d0;            // [2B+2BC, D] gradient w.r.t. the activated vertices
+  const float* d1;            // [2B+2BC, D] second addend (W_u / W_v data gradients) or null
+  const float* h_prev;        // [2B+2BC, D] pre-LayerNorm rows of the previous layer (ln)
+  const float* ln_gamma; const float* ln_beta;   // null: first layer, the rows are projection outputs
+  bf16* out_hi; bf16* out_lo; // [2B+2BC, D]
+  float* partials;            // [vec_rows_ctas()][4][D]: ln -> (dgamma, dbeta, db_h, -); else (db_mt, db_mi, db_et, db_ei)
+};
+int vec_rows_bwd(cudaStream_t stream, const VecRowsBwdArgs& a);
+int vec_rows_ctas();
+int strided_colsum(cudaStream_t stream, const float* src, int count, long long stride, int n, float* out);
 
 // loss.cu
 size_t triplet_scratch_bytes(int B, int C);

@@ -37,32 +37,50 @@ LAYER_FIELDS = (
     ("w_h.weight", "w_h"), ("w_h.bias", "b_h"), ("w_u.weight", "w_u"), ("w_u.bias", "b_u"),
     ("w_v.weight", "w_v"), ("w_v.bias", "b_v"), ("layer_norm.weight", "ln_w"), ("layer_norm.bias", "ln_b"),
 )
+# gcn_edge_feature == "vector": w_m is a Linear too, created right after w_h (drin/model.py:111-116)
+LAYER_FIELDS_VECTOR = LAYER_FIELDS[:2] + (("w_m.weight", "w_m"), ("w_m.bias", "b_m")) + LAYER_FIELDS[2:]
 
 
-def param_keys(num_layers: int) -> List[str]:
+def layer_fields(vector_edges: bool = False):
+    return LAYER_FIELDS_VECTOR if vector_edges else LAYER_FIELDS
+
+
+def param_keys(num_layers: int, vector_edges: bool = False) -> List[str]:
     keys = [k for k, _ in VERTEX_KEYS]
     for l in range(num_layers):
-        keys += [f"gcn_layers.{l}.{s}" for s, _ in LAYER_FIELDS]
+        keys += [f"gcn_layers.{l}.{s}" for s, _ in layer_fields(vector_edges)]
     return keys
 
 
-def param_shapes(num_layers: int, D: int = 768, R: int = 2048) -> Dict[str, Tuple[int, ...]]:
+def param_shapes(num_layers: int, D: int = 768, R: int = 2048, vector_edges: bool = False) -> Dict[str, Tuple[int, ...]]:
     shapes = {
         VERTEX_KEYS[0][0]: (D, D), VERTEX_KEYS[1][0]: (D,), VERTEX_KEYS[2][0]: (D, D), VERTEX_KEYS[3][0]: (D,),
         VERTEX_KEYS[4][0]: (D, R), VERTEX_KEYS[5][0]: (D,), VERTEX_KEYS[6][0]: (D, R), VERTEX_KEYS[7][0]: (D,),
     }
+    H = D // 2 if vector_edges else D          # vector edges: w_u / w_v map D -> D/2 (model.py:113-116)
     for l in range(num_layers):
-        for s, _ in LAYER_FIELDS:
-            shapes[f"gcn_layers.{l}.{s}"] = (D, D) if s in ("w_h.weight", "w_u.weight", "w_v.weight") else (D,)
+        for s, _ in layer_fields(vector_edges):
+            if s in ("w_u.weight", "w_v.weight"):
+                shape = (H, D)
+            elif s in ("w_u.bias", "w_v.bias"):
+                shape = (H,)
+            elif s in ("w_h.weight", "w_m.weight"):
+                shape = (D, D)
+            else:
+                shape = (D,)
+            shapes[f"gcn_layers.{l}.{s}"] = shape
     return shapes
 
 
-def dead_param_keys(num_layers: int, static_edges: bool = False) -> List[str]:
+def dead_param_keys(num_layers: int, static_edges: bool = False, vector_edges: bool = False) -> List[str]:
     """Parameters that never receive a gradient in the reference (grad is None): the edge update of the
     last GCN layer is dead code (drin/model.py:131-134); with gcn_edge_type="static" no layer
-    runs an edge update (model.py:135-136)."""
+    runs an edge update (model.py:135-136).  With vector edges the edge update also owns w_m."""
     layers = range(num_layers) if static_edges else (num_layers - 1,)
-    return [f"gcn_layers.{l}.{s}" for l in layers for s in ("w_u.weight", "w_u.bias", "w_v.weight", "w_v.bias")]
+    names = ("w_u.weight", "w_u.bias", "w_v.weight", "w_v.bias")
+    if vector_edges:
+        names = ("w_m.weight", "w_m.bias") + names
+    return [f"gcn_layers.{l}.{s}" for l in layers for s in names]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -172,10 +190,12 @@ def inspect_batch(batch: Sequence[torch.Tensor], num_candidates_model: Optional[
 class Engine:
     """One instance per module: caches the workspace and marshals calls into the C ABI."""
 
-    def __init__(self, num_layers: int, edge_enabled: Sequence[float] = (1, 1, 1, 1), static_edges: bool = False):
+    def __init__(self, num_layers: int, edge_enabled: Sequence[float] = (1, 1, 1, 1), static_edges: bool = False,
+                 vector_edges: bool = False):
         self.lib = _lib.load()
         self.num_layers = int(num_layers)
         self.static_edges = bool(static_edges)
+        self.vector_edges = bool(vector_edges)
         self.edge_enabled = tuple(float(x) for x in edge_enabled)
         if len(self.edge_enabled) != 4:
             raise ValueError("gcn_edge_enabled must have 4 entries")
@@ -192,6 +212,7 @@ class Engine:
             cfg.edge_enabled[i] = self.edge_enabled[i]
         cfg.static_edges = int(self.static_edges)
         cfg.indexed = int(indexed)
+        cfg.vector_edges = int(self.vector_edges)
         return cfg
 
     @staticmethod
@@ -209,11 +230,11 @@ class Engine:
     def params(self, tensors: Dict[str, torch.Tensor], D: int, R: int) -> _lib.DrinParams:
         """tensors: state_dict-keyed fp32 CUDA tensors (parameters, or gradient buffers of the same shapes)."""
         s = _lib.DrinParams()
-        shapes = param_shapes(self.num_layers, D, R)
+        shapes = param_shapes(self.num_layers, D, R, self.vector_edges)
         for key, fld in VERTEX_KEYS:
             setattr(s, fld, self._checked(tensors, key, shapes[key]))
         for l in range(self.num_layers):
-            for suffix, fld in LAYER_FIELDS:
+            for suffix, fld in layer_fields(self.vector_edges):
                 key = f"gcn_layers.{l}.{suffix}"
                 setattr(s.layer[l], fld, self._checked(tensors, key, shapes[key]))
         return s

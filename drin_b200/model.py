@@ -43,17 +43,19 @@ def _read_args(overrides: dict) -> dict:
 
 
 def _check_supported(cfg: dict) -> None:
-    want = dict(gcn_edge_feature="scaler", gcn_vertex_activation="gelu",
+    want = dict(gcn_vertex_activation="gelu",
                 gcn_edge_activation="sigmoid", mention_final_layer_name="linear",
                 mention_final_representation="avg extract", entity_final_layer_name="linear",
                 entity_final_pooling="avg", online_bert=False)
     bad = {k: cfg[k] for k, v in want.items() if cfg[k] != v}
     if cfg["gcn_edge_type"] not in ("dynamic", "static"):
         bad["gcn_edge_type"] = cfg["gcn_edge_type"]
+    if cfg["gcn_edge_feature"] not in ("scaler", "vector"):
+        bad["gcn_edge_feature"] = cfg["gcn_edge_feature"]
     if bad:
         raise NotImplementedError(
-            f"drin_b200 implements scalar-edge DRIN (dynamic or static edges, any layer count / edge mask); "
-            f"unsupported settings: {bad} (see SURVEY.md section 8f)")
+            f"drin_b200 implements DRIN with scalar or vector edges (dynamic or static, any layer count / edge "
+            f"mask); unsupported settings: {bad} (see SURVEY.md section 8f)")
     if cfg["gcn_embed_dim"] != 768 or cfg["bert_embed_dim"] != 768:
         raise NotImplementedError("kernels are built for gcn_embed_dim = bert_embed_dim = 768")
     if cfg["mention_final_output_dim"] != cfg["gcn_embed_dim"] or cfg["entity_final_output_dim"] != cfg["gcn_embed_dim"]:
@@ -89,11 +91,14 @@ class _VertexEncoder(nn.Module):   # drin/model.py:19-24
 
 
 class _GCNLayer(nn.Module):        # drin/model.py:109-119
-    def __init__(self, D):
+    def __init__(self, D, vector_edges=False):
         super().__init__()
         self.w_h = nn.Linear(D, D)
-        self.w_u = nn.Linear(D, D)
-        self.w_v = nn.Linear(D, D)
+        if vector_edges:               # model.py:112: w_m is nn.Identity() (no parameters) for scalar edges
+            self.w_m = nn.Linear(D, D)
+        H = D // 2 if vector_edges else D
+        self.w_u = nn.Linear(D, H)
+        self.w_v = nn.Linear(D, H)
         self.layer_norm = nn.LayerNorm(D)
 
 
@@ -134,11 +139,13 @@ class Model(nn.Module):
         self.num_candidates_model = cfg["num_candidates_model"]
         # same creation order as upstream -> same weights under the same seed
         self.vertex_encoder = _VertexEncoder(D, Db, R)
-        self.gcn_layers = nn.ModuleList([_GCNLayer(D) for _ in range(self.num_gcn_layers)])
+        self.vector_edges = cfg["gcn_edge_feature"] == "vector"
+        self.gcn_layers = nn.ModuleList([_GCNLayer(D, self.vector_edges) for _ in range(self.num_gcn_layers)])
         self._param_names: List[str] = [n for n, _ in self.named_parameters()]
-        assert self._param_names == E.param_keys(self.num_gcn_layers), "state_dict keys drifted from the reference"
+        assert self._param_names == E.param_keys(self.num_gcn_layers, self.vector_edges), \
+            "state_dict keys drifted from the reference"
         self.static_edges = cfg["gcn_edge_type"] == "static"
-        self._dead = E.dead_param_keys(self.num_gcn_layers, self.static_edges)
+        self._dead = E.dead_param_keys(self.num_gcn_layers, self.static_edges, self.vector_edges)
         self._engine_obj: Optional[E.Engine] = None
         self._flat: Optional[torch.Tensor] = None
         self._flat_grad: Optional[torch.Tensor] = None
@@ -205,7 +212,8 @@ class Model(nn.Module):
     @property
     def _engine(self) -> E.Engine:
         if self._engine_obj is None:
-            self._engine_obj = E.Engine(self.num_gcn_layers, self.cfg["gcn_edge_enabled"], self.static_edges)
+            self._engine_obj = E.Engine(self.num_gcn_layers, self.cfg["gcn_edge_enabled"], self.static_edges,
+                                        self.vector_edges)
         return self._engine_obj
 
     # ---- the reference's forward signature (drin/model.py:164) ----------------------------------

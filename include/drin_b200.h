@@ -54,6 +54,11 @@ typedef struct drin_config {
   int32_t indexed;          /* 0: the 14 input tensors hold exactly this batch (row b = mention b);
                                1: they are resident feature TABLES and drin_inputs.mention_index /
                                entity_index select the rows of this batch (drin/data.py:85-108 on device) */
+  int32_t vector_edges;     /* 0: gcn_edge_feature "scaler" (args.py:33): one scalar per edge;
+                               1: "vector": every edge is a D-vector (model.py:202), messages are elementwise
+                               products (model.py:139-146) and the dynamic edge update is
+                               e' = sigmoid(W_m(cat[W_u u, W_v v] + e)) with W_u, W_v: D -> D/2 and
+                               W_m: D -> D (model.py:112-116,133,148-152)                  */
 } drin_config;
 
 /* The 14 model inputs in the order of drin/model.py:164-180 (= drin/data.py:110-125).  Feature tensors
@@ -84,11 +89,14 @@ typedef struct drin_inputs {
   const int64_t* entity_index;
 } drin_inputs;
 
-/* Parameters in state_dict order (drin/model.py:21-24,111-119,159-162); all fp32.
- * Per GCN layer l: w_h, b_h, w_u, b_u, w_v, b_v, ln_w, ln_b.  The same struct carries gradients. */
+/* Parameters (drin/model.py:21-24,111-119,159-162); all fp32.
+ * Per GCN layer l: w_h, b_h, w_u, b_u, w_v, b_v, ln_w, ln_b [D, D] / [D]; with vector edges w_u, w_v are
+ * [D/2, D] / [D/2] and w_m, b_m ([D, D], [D]; nn.Identity without parameters for scalar edges, model.py:112)
+ * are read as well.  The same struct carries gradients. */
 #define DRIN_MAX_LAYERS 8
 typedef struct drin_layer_params {
   float* w_h; float* b_h; float* w_u; float* b_u; float* w_v; float* b_v; float* ln_w; float* ln_b;
+  float* w_m; float* b_m;   /* vector edges only (NULL otherwise) */
 } drin_layer_params;
 typedef struct drin_params {
   float* w_mt; float* b_mt;   /* vertex_encoder.mention_text_encoder.final_layer.linear  [D, D], [D] */
@@ -114,8 +122,8 @@ int drin_forward(const drin_config* cfg, const drin_inputs* in, const drin_param
 
 /* Backward of drin_forward through every parameter (what loss.backward() does after train.py:34).
  * dscores: [B, C] fp32.  grads: same layout as params; every tensor is OVERWRITTEN except the last
- * layer's w_u/b_u/w_v/b_v, which receive no gradient in the reference (grad is None) and are left
- * untouched.  Must follow a drin_forward with training = 1 on the same workspace. */
+ * layer's w_u/b_u/w_v/b_v (and w_m/b_m with vector edges), which receive no gradient in the reference
+ * (grad is None) and are left untouched.  Must follow a drin_forward with training = 1 on the same workspace. */
 int drin_backward(const drin_config* cfg, const drin_inputs* in, const drin_params* params, void* workspace,
                   size_t workspace_bytes, const float* dscores, const drin_params* grads, void* stream);
 
@@ -186,7 +194,7 @@ void drin_profile_enable(int32_t on);
 int drin_profile_collect(double* ms, double* flops, double* bytes, long long* count);
 
 /* Test hook: device pointer / shape of a named fp32 intermediate ("edges0", "x0", "h", "xm", "fu", "g",
- * "edges_out", "dz") inside a workspace planned for cfg.  Not part of the drop-in surface. */
+ * "edges_out", "dz"; vector edges: "xa", "fv", "q") inside a workspace planned for cfg.  Not part of the drop-in surface. */
 int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name, int32_t layer, void** ptr,
                       int64_t* rows, int64_t* cols);
 

@@ -45,6 +45,7 @@ def gcn_keys(layer: int) -> Dict[str, str]:
         "w_u": p + "w_u.weight", "b_u": p + "w_u.bias",
         "w_v": p + "w_v.weight", "b_v": p + "w_v.bias",
         "ln_w": p + "layer_norm.weight", "ln_b": p + "layer_norm.bias",
+        "w_m": p + "w_m.weight", "b_m": p + "w_m.bias",      # gcn_edge_feature == "vector" only (model.py:112)
     }
 
 
@@ -58,6 +59,7 @@ class DrinConfig:
     resnet_embed_dim: int = 2048             # args.py:52
     gcn_edge_enabled: Tuple[float, ...] = (1, 1, 1, 1)   # args.py:34
     gcn_edge_type: str = "dynamic"           # args.py:32 ("dynamic" | "static")
+    gcn_edge_feature: str = "scaler"         # args.py:33 ("scaler" | "vector")
     triplet_margin: float = 0.25             # args.py:117,125
 
 
@@ -66,7 +68,10 @@ def state_dict_keys(cfg: DrinConfig) -> List[str]:
     keys = [K_MT_W, K_MT_B, K_ET_W, K_ET_B, K_MI_W, K_MI_B, K_EI_W, K_EI_B]
     for l in range(cfg.num_gcn_layers):
         k = gcn_keys(l)
-        keys += [k["w_h"], k["b_h"], k["w_u"], k["b_u"], k["w_v"], k["b_v"], k["ln_w"], k["ln_b"]]
+        keys += [k["w_h"], k["b_h"]]
+        if cfg.gcn_edge_feature == "vector":          # w_m is a Linear only for vector edges (model.py:112)
+            keys += [k["w_m"], k["b_m"]]
+        keys += [k["w_u"], k["b_u"], k["w_v"], k["b_v"], k["ln_w"], k["ln_b"]]
     return keys
 
 
@@ -88,8 +93,11 @@ def init_state(cfg: DrinConfig, seed: int = 0) -> Dict[str, Tensor]:
     for l in range(cfg.num_gcn_layers):
         k = gcn_keys(l)
         lin(k["w_h"], k["b_h"], D, D)   # model.py:111
-        lin(k["w_u"], k["b_u"], D, D)   # model.py:113-116 (list comprehension: w_u then w_v)
-        lin(k["w_v"], k["b_v"], D, D)
+        vec = cfg.gcn_edge_feature == "vector"
+        if vec:
+            lin(k["w_m"], k["b_m"], D, D)   # model.py:112 (Identity, no parameters, for scalar edges)
+        lin(k["w_u"], k["b_u"], D // 2 if vec else D, D)   # model.py:113-116 (list comprehension: w_u then w_v)
+        lin(k["w_v"], k["b_v"], D // 2 if vec else D, D)
         sd[k["ln_w"]], sd[k["ln_b"]] = torch.ones(D), torch.zeros(D)   # model.py:119
     return sd
 
@@ -172,8 +180,40 @@ def edge_encode(batch, loops=False) -> Tuple[Tensor, Tensor]:
     return tt, sim / (den + 1e-9)                                     # model.py:92
 
 
+def gcn_layer_vector(sd, layer: int, cfg: DrinConfig, V: List[Tensor], E: List[Tensor]):
+    """GCNLayer.forward for gcn_edge_feature == "vector", drin/model.py:121-153: every edge is a [B, C, D]
+    tensor, messages are elementwise products (model.py:139-146 without the scalar expand), and the dynamic
+    edge update is e' = sigmoid(W_m(cat[W_u u, W_v v] + e)) with W_u, W_v: D -> D/2 (model.py:112-116,148-152)."""
+    k = gcn_keys(layer)
+    mt, mi, et, ei = V
+    E = [e * m for e, m in zip(E, cfg.gcn_edge_enabled)]              # model.py:122
+    e0, e1, e2, e3 = E                                                # order tt, ti, it, ii; each [B, C, D]
+    a_mt = (e0 * et).mean(1) + (e1 * ei).mean(1)
+    a_mi = (e2 * et).mean(1) + (e3 * ei).mean(1)
+    a_et = e0 * mt.unsqueeze(1) + e2 * mi.unsqueeze(1)
+    a_ei = e1 * mt.unsqueeze(1) + e3 * mi.unsqueeze(1)
+
+    def upd(a, x):                                                    # model.py:128
+        h = F.linear(a + x, sd[k["w_h"]], sd[k["b_h"]])
+        return F.gelu(F.layer_norm(h, (h.shape[-1],), sd[k["ln_w"]], sd[k["ln_b"]], 1e-5))
+
+    newV = [upd(a_mt, mt), upd(a_mi, mi), upd(a_et, et), upd(a_ei, ei)]
+    if cfg.gcn_edge_type != "dynamic":                                # model.py:135-136
+        return newV, E
+    C = et.shape[1]
+    fu = {0: F.linear(mt, sd[k["w_u"]], sd[k["b_u"]]), 1: F.linear(mi, sd[k["w_u"]], sd[k["b_u"]])}     # [B, D/2]
+    fv = {2: F.linear(et, sd[k["w_v"]], sd[k["b_v"]]), 3: F.linear(ei, sd[k["w_v"]], sd[k["b_v"]])}     # [B, C, D/2]
+    newE = []
+    for e, (ui, vi) in zip(E, ((0, 2), (0, 3), (1, 2), (1, 3))):
+        m = torch.cat([fu[ui].unsqueeze(1).expand(-1, C, -1), fv[vi]], dim=-1)        # model.py:150-152
+        newE.append(torch.sigmoid(F.linear(m + e, sd[k["w_m"]], sd[k["b_m"]])))       # model.py:133
+    return newV, newE
+
+
 def gcn_layer(sd, layer: int, cfg: DrinConfig, V: List[Tensor], E: List[Tensor]):
     """GCNLayer.forward for scalar edges (dynamic or static edge type), drin/model.py:121-153."""
+    if cfg.gcn_edge_feature == "vector":
+        return gcn_layer_vector(sd, layer, cfg, V, E)
     k = gcn_keys(layer)
     mt, mi, et, ei = V
     C = et.shape[1]
@@ -208,6 +248,8 @@ def forward(sd: Dict[str, Tensor], batch: Sequence[Tensor], cfg: DrinConfig, loo
     tt, ii = edge_encode(batch, loops)
     miet, mtei = batch[12], batch[13]
     E = [tt, mtei / 100, miet / 100, ii]                              # model.py:201-204
+    if cfg.gcn_edge_feature == "vector":                              # model.py:202: scalars broadcast over D
+        E = [e.unsqueeze(-1).expand(-1, -1, cfg.gcn_embed_dim) for e in E]
     for l in range(cfg.num_gcn_layers):                               # model.py:205-206
         V, E = gcn_layer(sd, l, cfg, V, E)
     return cosine(V[0].unsqueeze(1), V[2])                            # model.py:207-209

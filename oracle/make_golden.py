@@ -45,6 +45,18 @@ CASES = [
          overrides=dict(gcn_edge_type="static")),
     dict(name="wd_b6_static_l3_mask", dataset="wikidiverse", B=6, cands=10, seed=11, weights="spread",
          overrides=dict(gcn_edge_type="static", num_gcn_layers=3, gcn_edge_enabled=[1, 1, 0, 1])),
+    # gcn_edge_feature = "vector" (args.py:33): [B, C, D] edges, W_m edge update, D/2-wide W_u / W_v
+    dict(name="wd_b8_vector", dataset="wikidiverse", B=8, cands=10, seed=12, weights="spread",
+         overrides=dict(gcn_edge_feature="vector")),
+    dict(name="wd_b6_vector_l3_mask", dataset="wikidiverse", B=6, cands=10, seed=13, weights="spread",
+         overrides=dict(gcn_edge_feature="vector", num_gcn_layers=3, gcn_edge_enabled=[1, 0, 1, 1])),
+    dict(name="wm_b3_c6_vector", dataset="wikimel", B=3, cands=5, seed=14, weights="spread",
+         batch_kw=dict(entity_tokens=16, mention_tokens=32), entity_tokens=16,
+         overrides=dict(gcn_edge_feature="vector")),
+    dict(name="wd_b5_vector_static", dataset="wikidiverse", B=5, cands=10, seed=15, weights="spread",
+         overrides=dict(gcn_edge_feature="vector", gcn_edge_type="static")),
+    dict(name="wd_b4_vector_l1", dataset="wikidiverse", B=4, cands=10, seed=16, weights="spread",
+         overrides=dict(gcn_edge_feature="vector", num_gcn_layers=1)),
 ]
 
 
@@ -61,6 +73,7 @@ def run_case(case):
                        num_gcn_layers=ov.get("num_gcn_layers", 2),
                        gcn_edge_enabled=tuple(ov.get("gcn_edge_enabled", (1, 1, 1, 1))),
                        gcn_edge_type=ov.get("gcn_edge_type", "dynamic"),
+                       gcn_edge_feature=ov.get("gcn_edge_feature", "scaler"),
                        triplet_margin=ov.get("triplet_margin", 0.25))
     batch = make_batch(case["dataset"], case["B"], case["seed"], case["cands"], **case.get("batch_kw", {}))
     sd = O.init_state(cfg, seed=0)

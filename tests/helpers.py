@@ -11,7 +11,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_model_cases():
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")) if "triplet_loss" not in p)
+    """Scalar-edge cases first (tests index into them), then the gcn_edge_feature="vector" cases."""
+    paths = [p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")) if "triplet_loss" not in p]
+    return sorted(paths, key=lambda p: ("vector" in os.path.basename(p), p))
 
 
 def load_case(path):
@@ -23,6 +25,7 @@ def load_case(path):
                        num_gcn_layers=ov.get("num_gcn_layers", 2),
                        gcn_edge_enabled=tuple(ov.get("gcn_edge_enabled", (1, 1, 1, 1))),
                        gcn_edge_type=ov.get("gcn_edge_type", "dynamic"),
+                       gcn_edge_feature=ov.get("gcn_edge_feature", "scaler"),
                        triplet_margin=ov.get("triplet_margin", 0.25))
     batch = make_batch(case["dataset"], case["B"], case["seed"], case["cands"], **case.get("batch_kw", {}))
     sd = O.init_state(cfg, seed=0)

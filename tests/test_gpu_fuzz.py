@@ -1,5 +1,5 @@
 """Seeded shape / configuration fuzzing of the whole train step against the CPU oracle: odd batch sizes (1, primes),
-2..24 candidate slots, 1-3 GCN layers, edge masks, static / dynamic edges, both dataset layouts, ragged WikiMEL entity
+2..24 candidate slots, 1-4 GCN layers, edge masks, static / dynamic edges, scalar / vector edges, both dataset layouts, ragged WikiMEL entity
 lengths (down to the 3-token minimum) and both kernel families (CTA-per-mention and warp-per-mention)."""
 import ctypes as C
 import random
@@ -33,18 +33,33 @@ def _cases():
             seed=100 + i,
             kw=dict(entity_tokens=rng.choice([4, 5, 16]), mention_tokens=rng.choice([24, 32])) if wm else {},
         ))
+    for c in out:
+        c["vector"] = False
+    rng = random.Random(20251019)            # gcn_edge_feature="vector" cases (appended: the cases above keep their draws)
+    for i in range(10):
+        wm = i % 3 == 2
+        out.append(dict(
+            dataset="wikimel" if wm else "wikidiverse",
+            B=rng.choice([1, 2, 3, 5, 7, 13, 33]),
+            cands=rng.choice([1, 2, 3, 6, 10, 23]) if not wm else rng.choice([1, 4, 9]),
+            layers=rng.choice([2, 2, 3, 4]),
+            mask=rng.choice([(1, 1, 1, 1), (1, 1, 1, 1), (0, 1, 1, 1), (1, 0, 0, 1), (1, 1, 1, 0)]),
+            static=False, vector=True, variant=-1, seed=200 + i,
+            kw=dict(entity_tokens=rng.choice([4, 5, 16]), mention_tokens=rng.choice([24, 32])) if wm else {},
+        ))
     return out
 
 
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: f"{c['dataset'][:5]}-B{c['B']}-C{c['cands'] + 1}-L{c['layers']}-"
-                                                         f"{'st' if c['static'] else 'dy'}-v{c['variant']}")
+                                                         f"{'st' if c['static'] else 'dy'}{'-vec' if c['vector'] else ''}-v{c['variant']}")
 def test_fuzzed_train_step_matches_oracle(case):
     lib = _lib.load()
     for name in OPTIONS:
         _lib.check(lib.drin_debug_option(name.encode(), C.c_int32(case["variant"])), "drin_debug_option")
     try:
         cfg = O.DrinConfig(num_candidates_model=case["cands"] + 1, num_gcn_layers=case["layers"],
-                           gcn_edge_enabled=case["mask"], gcn_edge_type="static" if case["static"] else "dynamic")
+                           gcn_edge_enabled=case["mask"], gcn_edge_type="static" if case["static"] else "dynamic",
+                           gcn_edge_feature="vector" if case["vector"] else "scaler")
         batch = make_batch(case["dataset"], case["B"], case["seed"], case["cands"], **case["kw"])
         if case["dataset"] == "wikimel":          # ragged entity lengths incl. the 3-token minimum (CLS, one token, SEP)
             Le = batch[8].shape[-1]
@@ -53,7 +68,8 @@ def test_fuzzed_train_step_matches_oracle(case):
         sd = spread_weights(O.init_state(cfg, 0))
         s_ref, l_ref, g_ref = O.train_step_grads(sd, batch[:-1], batch[-1], cfg)
         model = drin_b200.Model(num_gcn_layers=cfg.num_gcn_layers, gcn_edge_enabled=cfg.gcn_edge_enabled,
-                                gcn_edge_type=cfg.gcn_edge_type, num_candidates_model=cfg.num_candidates_model)
+                                gcn_edge_type=cfg.gcn_edge_type, gcn_edge_feature=cfg.gcn_edge_feature,
+                                num_candidates_model=cfg.num_candidates_model)
         model.load_state_dict(sd)
         model = model.cuda()
         db = [t.cuda() for t in batch]

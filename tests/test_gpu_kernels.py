@@ -64,6 +64,18 @@ def test_gemm_layouts(layout, planes):
             assert perr < 3e-5
 
 
+def test_gemm_half_width_shapes_of_the_vector_edge_update():
+    """W_u / W_v of the vector-edge update map 768 -> 384 (drin/model.py:113-116): N = 384 ends inside a 256-column
+    tile (ragged N tile, TMA zero fill of the missing B rows), K = 384 is six k-blocks; both cta_group variants."""
+    for planes in (1, 2):
+        tol = 2e-5 if planes == 2 else 5e-6
+        for layout, (M, N, K), ks in ((0, (16, 384, 768), 1), (0, (176, 384, 768), 1), (0, (1000, 384, 768), 1),
+                                      (1, (16, 768, 384), 1), (1, (520, 768, 384), 1),
+                                      (2, (384, 768, 16), 1), (2, (384, 768, 1100), 8), (2, (384, 768, 176), 2)):
+            err, _ = _gemm(layout, planes, M, N, K, ksplit=ks, bias=(layout == 0))
+            assert err < tol, (layout, planes, M, N, K, err)
+
+
 def test_gemm_split_k_is_deterministic_and_exact():
     e1, _ = _gemm(2, 2, 768, 2048, 5000, ksplit=3)
     e2, _ = _gemm(2, 2, 768, 768, 9000, ksplit=8)
@@ -226,3 +238,47 @@ def test_forward_intermediates_stage_by_stage(dataset, B, cands, layers, kw, var
     finally:
         for name in ("score_fwd_variant", "layer_fwd_variant"):
             _lib.check(_lib.load().drin_debug_option(name.encode(), C.c_int32(-1)), "drin_debug_option")
+
+
+@pytest.mark.parametrize("dataset,B,cands,layers,mask,kw", [
+    ("wikidiverse", 9, 10, 2, (1, 1, 1, 1), {}), ("wikidiverse", 5, 10, 3, (1, 0, 1, 1), {}),
+    ("wikimel", 3, 5, 2, (1, 1, 1, 1), dict(entity_tokens=16, mention_tokens=32))])
+def test_vector_edge_forward_stage_by_stage(dataset, B, cands, layers, mask, kw):
+    """gcn_edge_feature="vector" (drin/model.py:112-116,133,139-152): per layer the activated vertices entering it
+    (xa), W_v v (fv), the PRE-sigmoid edge outputs q = W_m(cat[fu, fv] + e) + b_m and the W_h outputs, then scores."""
+    import torch.nn.functional as F
+
+    from drin_b200.synthetic import spread_weights
+    cfg = O.DrinConfig(num_candidates_model=cands + 1, num_gcn_layers=layers, gcn_edge_feature="vector",
+                       gcn_edge_enabled=mask)
+    batch = make_batch(dataset, B, 41, cands, **kw)
+    sd = spread_weights(O.init_state(cfg, 0))
+    V = O.vertex_encode(sd, batch[:-1])
+    tt, ii = O.edge_encode(batch[:-1])
+    El = [e.unsqueeze(-1).expand(-1, -1, 768) for e in (tt, batch[13] / 100, batch[12] / 100, ii)]
+    eng = E.Engine(layers, mask, vector_edges=True)
+    scores, ctx = eng.forward([t.cuda() for t in batch[:-1]], {k: v.cuda() for k, v in sd.items()}, training=False)
+    Vl = V
+    for l in range(layers):
+        k = O.gcn_keys(l)
+        xa = torch.cat([Vl[0], Vl[1], Vl[2].flatten(0, 1), Vl[3].flatten(0, 1)])
+        assert rel_err(eng.debug_buffer(ctx, "xa", l).cpu(), xa) < 2e-5, l
+        if l < layers - 1:
+            fv = torch.cat([F.linear(Vl[2], sd[k["w_v"]], sd[k["b_v"]]).flatten(0, 1),
+                            F.linear(Vl[3], sd[k["w_v"]], sd[k["b_v"]]).flatten(0, 1)])
+            assert rel_err(eng.debug_buffer(ctx, "fv", l).cpu(), fv) < 2e-5, l
+            fu = torch.cat([F.linear(Vl[0], sd[k["w_u"]], sd[k["b_u"]]), F.linear(Vl[1], sd[k["w_u"]], sd[k["b_u"]])])
+            assert rel_err(eng.debug_buffer(ctx, "fu", l).cpu(), fu) < 2e-5, l
+        Vn, En = O.gcn_layer(sd, l, cfg, Vl, El)
+        h = eng.debug_buffer(ctx, "h", l).cpu()
+        act = F.gelu(F.layer_norm(h, (h.shape[-1],), sd[k["ln_w"]], sd[k["ln_b"]], 1e-5))
+        if l < layers - 1:
+            want = torch.cat([Vn[0], Vn[1], Vn[2].flatten(0, 1), Vn[3].flatten(0, 1)])
+            q = eng.debug_buffer(ctx, "q", l).cpu()
+            got_e = torch.sigmoid(q).view(4, B, cands + 1, 768)
+            assert rel_err(got_e, torch.stack(En)) < 2e-5, l
+        else:
+            want = torch.cat([Vn[0], Vn[2].flatten(0, 1)])
+        assert rel_err(act, want) < 2e-5, l
+        Vl, El = Vn, En
+    assert rel_err(scores.cpu(), O.cosine(Vl[0].unsqueeze(1), Vl[2])) < 1e-5

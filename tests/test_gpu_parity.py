@@ -41,7 +41,8 @@ VARIANT_OPTIONS = ("score_bwd_variant", "score_fwd_variant", "layer_fwd_variant"
 
 def _cuda_model(cfg, sd):
     m = drin_b200.Model(num_gcn_layers=cfg.num_gcn_layers, gcn_edge_enabled=cfg.gcn_edge_enabled,
-                        gcn_edge_type=cfg.gcn_edge_type, num_candidates_model=cfg.num_candidates_model)
+                        gcn_edge_type=cfg.gcn_edge_type, gcn_edge_feature=cfg.gcn_edge_feature,
+                        num_candidates_model=cfg.num_candidates_model)
     m.load_state_dict(sd)
     return m.cuda()
 

@@ -54,7 +54,7 @@ def test_model_is_a_drop_in_for_the_reference_constructor():
 
 
 def test_unsupported_configurations_fail_loudly():
-    for kw in (dict(gcn_edge_feature="vector"), dict(gcn_edge_type="learned"), dict(gcn_vertex_activation="relu"),
+    for kw in (dict(gcn_edge_feature="matrix"), dict(gcn_edge_type="learned"), dict(gcn_vertex_activation="relu"),
                dict(gcn_embed_dim=512)):
         with pytest.raises(NotImplementedError):
             drin_b200.Model(**kw)
@@ -84,3 +84,22 @@ def test_param_key_tables():
     # gcn_edge_type="static": no layer has an edge update (drin/model.py:135-136)
     assert len(E.dead_param_keys(3, static_edges=True)) == 12
     assert int(drin_b200.Model(gcn_edge_type="static").dead_mask().sum()) == 4 * (768 * 768 + 768)
+
+
+def test_vector_edge_model_is_a_drop_in_for_the_reference_constructor():
+    """gcn_edge_feature="vector" (args.py:33): w_m becomes a Linear created right after w_h, w_u / w_v map D -> D/2
+    (drin/model.py:111-116).  Same keys, creation order and seeded weights as the reference (pinned by make_golden.py)."""
+    cfg = O.DrinConfig(gcn_edge_feature="vector")
+    torch.manual_seed(0)
+    m = drin_b200.Model(gcn_edge_feature="vector")
+    sd = O.init_state(cfg, 0)
+    assert list(m.state_dict().keys()) == O.state_dict_keys(cfg) == E.param_keys(2, vector_edges=True)
+    assert all(torch.equal(sd[k], v) for k, v in m.state_dict().items())
+    shapes = E.param_shapes(2, vector_edges=True)
+    assert shapes["gcn_layers.0.w_u.weight"] == (384, 768) and shapes["gcn_layers.0.w_m.weight"] == (768, 768)
+    assert all(tuple(v.shape) == shapes[k] for k, v in sd.items())
+    # the last layer's edge update is dead code: w_m, w_u, w_v of layer 1 never get a gradient
+    dead = E.dead_param_keys(2, vector_edges=True)
+    assert dead == [f"gcn_layers.1.{s}" for s in ("w_m.weight", "w_m.bias", "w_u.weight", "w_u.bias", "w_v.weight",
+                                                  "w_v.bias")]
+    assert int(m.dead_mask().sum()) == 768 * 768 + 768 + 2 * (384 * 768 + 384)
