@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--dataset wikidiverse|wikimel] [--batch B_per_gpu] [--precision fp32|bf16]
+                    [--edge-feature scaler|vector]
 
 One "step" = one pass of the hot path over one batch of synthetic features:
   train step = forward + TripletLoss + backward (+ gradient all-reduce at N > 1) + Adam   (headline)
@@ -45,6 +46,8 @@ def parse_args():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--cpu-batch", type=int, default=512,
                     help="mentions per step of the CPU reference sample (larger batches favour the CPU: 553 m/s at 32, 872 at 512)")
+    ap.add_argument("--edge-feature", default="scaler", choices=["scaler", "vector"],
+                    help="gcn_edge_feature (args.py:33); the headline is the reference default, scalar edges")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -62,8 +65,10 @@ def algorithmic_bytes_per_mention(C, wm, D=768, R=2048, P=49, Om=3, Oe=1, Le=64,
     return b
 
 
-def gemm_flops_per_mention(C, train, D=768, R=2048):
+def gemm_flops_per_mention(C, train, D=768, R=2048, vector=False):
     u, r = 2 * D * D, 2 * R * D
+    if vector:   # per unit: projections u + r; layer 1: W_h 2u, W_u | W_v (D -> D/2) on both kinds u, W_m on 4 edges 4u;
+        return (1 + C) * ((2 * r + 26 * u) if train else (r + 9 * u))   # layer 2: W_h on the text kind u
     return (1 + C) * ((2 * r + 17 * u) if train else (r + 6 * u))     # reference-necessary
 
 
@@ -109,14 +114,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port, loop-faithful like the reference's Python loops)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(dataset, batch, steps, warmup, loops=True):
+def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="scaler"):
     import torch
     from drin_b200.synthetic import make_batch
     from oracle import drin_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
     cands = 10 if dataset == "wikidiverse" else 100
-    cfg = O.DrinConfig(num_candidates_model=cands + 1)
+    cfg = O.DrinConfig(num_candidates_model=cands + 1, gcn_edge_feature=edge_feature)
     b = make_batch(dataset, batch, 0, cands)
     sd = O.init_state(cfg, 0)
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -155,7 +160,7 @@ def run_reference(args):
     if rank != 0:
         return
     B = args.cpu_batch if args.cpu_batch else 512
-    r = cpu_reference_run(args.dataset, B, args.steps, args.warmup, loops=True)
+    r = cpu_reference_run(args.dataset, B, args.steps, args.warmup, loops=True, edge_feature=args.edge_feature)
     cands = 10 if args.dataset == "wikidiverse" else 100
     sample = (f"oracle port of the reference (per-item Python loops kept), {args.dataset}-shaped batch of {B} mentions per "
               f"step, fwd+TripletLoss+bwd+Adam, {args.warmup} warm-up + {args.steps} timed steps, torch CPU "
@@ -207,7 +212,7 @@ def run_ours(args):
     feats = (0, 4, 5, 7, 9, 10)
 
     torch.manual_seed(0)
-    model = drin_b200.Model(num_candidates_model=Cn).to(dev)
+    model = drin_b200.Model(num_candidates_model=Cn, gcn_edge_feature=args.edge_feature).to(dev)
     trainer = drin_b200.Trainer(model, lr=1e-3, margin=0.25)
     batch = make_batch(args.dataset, B, seed=1000 + rank, num_candidates=cands, device=str(dev), generate_on_device=True)
     if bf16:
@@ -393,8 +398,8 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.dataset, args.cpu_batch, 12, 2, loops=True)
-        rv = cpu_reference_run(args.dataset, args.cpu_batch, 6, 1, loops=False)
+        r = cpu_reference_run(args.dataset, args.cpu_batch, 12, 2, loops=True, edge_feature=args.edge_feature)
+        rv = cpu_reference_run(args.dataset, args.cpu_batch, 6, 1, loops=False, edge_feature=args.edge_feature)
         cpu = {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": (f"oracle port (reference-style Python loops), {args.dataset}-shaped batch of {args.cpu_batch}, "
                           f"fwd+loss+bwd+Adam, 2 warm-up + 12 timed steps, {r['threads']} torch threads"),
@@ -405,6 +410,7 @@ def run_ours(args):
         "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if bf16 else "f32 (GEMMs as 3-pass split-bf16 on tcgen05, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": f"DRIN training step, {args.dataset}-shaped synthetic features, C={Cn} candidate slots",
+                   "gcn_edge_feature": args.edge_feature,
                    "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": f"inputs {in_bytes / 2**20:.0f} MiB per step per GPU, larger than the 126 MB L2 (no flush needed)",
                    "input_bytes_per_mention": in_bytes / B,
@@ -413,7 +419,7 @@ def run_ours(args):
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "ranking": ranking,
         "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         "ms_per_step_with_stage_events": ms_train_profiled,
-        "necessary_gemm_tflops_of_step": gemm_flops_per_mention(Cn, True) * B / (ms_train * 1e-3) / 1e12,
+        "necessary_gemm_tflops_of_step": gemm_flops_per_mention(Cn, True, vector=args.edge_feature == "vector") * B / (ms_train * 1e-3) / 1e12,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

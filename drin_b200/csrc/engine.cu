@@ -91,8 +91,8 @@ static int plan_vector(const drin_config& c, Bump& m, Workspace& ws) {
     ws.colsum_ctas = backward_ctas();
     ws.colsum_floats = (size_t)2 * ws.colsum_ctas * 3 * D;        // score_bwd (and its sliced mention finish)
     ws.colsum = m.take<float>(ws.colsum_floats);
-    ws.vec_part = m.take<float>((size_t)vec_layer_ctas() * 2 * D);
-    ws.rows_part = m.take<float>((size_t)vec_rows_ctas() * 4 * D);
+    ws.vec_part = m.take<float>((size_t)L * vec_layer_ctas() * 2 * D);
+    ws.rows_part = m.take<float>((size_t)L * vec_rows_ctas() * 4 * D);
   }
   ws.bytes = align_up(m.off, 256);
   return DRIN_OK;

@@ -71,8 +71,8 @@ struct Workspace {
   float* dm = nullptr;               // [4BC, D] gradient w.r.t. m
   Planes dq_p;                       // [4BC, D] gradient w.r.t. the pre-sigmoid edge outputs of the layer below
   Planes dfv_p;                      // [2BC, D/2]; dfu_p above is [2B, D/2]
-  float* vec_part = nullptr;         // [vec_layer_ctas()][2][D] column partials of vec_layer_bwd
-  float* rows_part = nullptr;        // [vec_rows_ctas()][4][D] column partials of vec_rows_bwd
+  float* vec_part = nullptr;         // [L][vec_layer_ctas()][2][D] column partials of vec_layer_bwd (one region per layer:
+  float* rows_part = nullptr;        // [L][vec_rows_ctas()][4][D]  ... of vec_rows_bwd       all reduced by one launch)
 };
 
 // vector edges with static edges (or one layer) never leave the scalar representation: model.py:135-136 passes the

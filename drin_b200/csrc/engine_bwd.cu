@@ -67,9 +67,16 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
   const long long B = c.batch, C = c.candidates, BC = B * C;
   const int D = c.embed_dim, H = D / 2, L = c.gcn_layers;
   const size_t part_floats = (size_t)ws.colsum_ctas * 3 * D;
+  StridedColsumJobs cs;          // bias / LayerNorm gradients: per-CTA partials of every layer, reduced by one launch
+  auto colsum = [&](const float* src, int count, long long stride, int n, float* out) {
+    if (!out) return fail(DRIN_ERR_ARG, "gradient buffer is null");
+    return cs.add(src, count, stride, n, out) ? fail(DRIN_ERR_ARG, "internal: too many column-sum jobs") : (int)DRIN_OK;
+  };
   for (int l = L - 1; l >= 0; --l) {
     const LayerWs& lw = ws.layer[l];
     const drin_layer_params& lg = grads.layer[l];
+    float* vec_part = ws.vec_part + (size_t)l * vec_layer_ctas() * 2 * D;
+    float* rows_part = ws.rows_part + (size_t)l * vec_rows_ctas() * 4 * D;
     if (l == L - 1) {
       const drin_layer_params& lp = p.layer[l];
       ScoreBwdArgs sa{};
@@ -109,13 +116,13 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
       va.dfv_hi = ws.dfv_p.hi; va.dfv_lo = ws.dfv_p.lo;
     }
     if (l > 0) { va.dq_hi = ws.dq_p.hi; va.dq_lo = ws.dq_p.lo; }      // safe: dm / dW_m above already consumed dq_p
-    va.partials = ws.vec_part;
+    va.partials = vec_part;
     int prow = 0;
     DRIN_TRY(vec_layer_bwd(stream, va, &prow));
-    if (l > 0) DRIN_TRY(strided_colsum(stream, ws.vec_part, prow, 2 * D, D, grads.layer[l - 1].b_m));
+    if (l > 0) DRIN_TRY(colsum(vec_part, prow, 2 * D, D, grads.layer[l - 1].b_m));
     if (lw.dyn) {
-      DRIN_TRY(strided_colsum(stream, ws.vec_part + D, prow, 2 * D, H, lg.b_u));
-      DRIN_TRY(strided_colsum(stream, ws.vec_part + D + H, prow, 2 * D, H, lg.b_v));
+      DRIN_TRY(colsum(vec_part + D, prow, 2 * D, H, lg.b_u));
+      DRIN_TRY(colsum(vec_part + D + H, prow, 2 * D, H, lg.b_v));
       DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfu_p, 2 * B, H), op(lw.xa_p, 2 * B, D), H, D, 2 * B, lg.w_u));
       DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfv_p, 2 * BC, H), op(lw.xa_p, 2 * BC, D, 2 * B), H, D, 2 * BC, lg.w_v));
       GemmEpilogue ex;
@@ -128,7 +135,7 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
     ra.B = B; ra.BC = BC; ra.D = D;
     ra.d0 = ws.dxa;
     ra.d1 = lw.dyn ? ws.dxuv : nullptr;
-    ra.partials = ws.rows_part;
+    ra.partials = rows_part;
     const long long pstride = 4 * D;
     if (l > 0) {
       const drin_layer_params& pg = grads.layer[l - 1];
@@ -136,19 +143,19 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
       ra.ln_gamma = p.layer[l - 1].ln_w; ra.ln_beta = p.layer[l - 1].ln_b;
       ra.out_hi = ws.dh.hi; ra.out_lo = ws.dh.lo;
       DRIN_TRY(vec_rows_bwd(stream, ra));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part, vec_rows_ctas(), pstride, D, pg.ln_w));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part + D, vec_rows_ctas(), pstride, D, pg.ln_b));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part + 2 * D, vec_rows_ctas(), pstride, D, pg.b_h));
+      DRIN_TRY(colsum(rows_part, vec_rows_ctas(), pstride, D, pg.ln_w));
+      DRIN_TRY(colsum(rows_part + D, vec_rows_ctas(), pstride, D, pg.ln_b));
+      DRIN_TRY(colsum(rows_part + 2 * D, vec_rows_ctas(), pstride, D, pg.b_h));
     } else {
       ra.out_hi = ws.dx0.hi; ra.out_lo = ws.dx0.lo;
       DRIN_TRY(vec_rows_bwd(stream, ra));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part, vec_rows_ctas(), pstride, D, grads.b_mt));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part + D, vec_rows_ctas(), pstride, D, grads.b_mi));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part + 2 * D, vec_rows_ctas(), pstride, D, grads.b_et));
-      DRIN_TRY(strided_colsum(stream, ws.rows_part + 3 * D, vec_rows_ctas(), pstride, D, grads.b_ei));
+      DRIN_TRY(colsum(rows_part, vec_rows_ctas(), pstride, D, grads.b_mt));
+      DRIN_TRY(colsum(rows_part + D, vec_rows_ctas(), pstride, D, grads.b_mi));
+      DRIN_TRY(colsum(rows_part + 2 * D, vec_rows_ctas(), pstride, D, grads.b_et));
+      DRIN_TRY(colsum(rows_part + 3 * D, vec_rows_ctas(), pstride, D, grads.b_ei));
     }
   }
-  return DRIN_OK;
+  return strided_colsum_multi(stream, cs);
 }
 
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,

@@ -10,6 +10,8 @@
 // gradients) live in registers.  The three contractions of the layer (W_h, W_u / W_v, W_m) are tcgen05 GEMMs fed
 // by the bf16 planes these kernels emit (engine.cu).  Edges travel between layers PRE-sigmoid (`q`), the consumer
 // applies sigmoid and the enable mask (model.py:122) on the fly; the first layer reads the scalar input edges.
+// The [4BC, D] edge matrices (m, q, dm, dq) are CANDIDATE-major, row r * 4 + k: the four edge vectors of a candidate
+// are one contiguous 12 KB block, so a CTA walks 8 HBM streams instead of 17 (the GEMMs do not care about row order).
 #include "kernels.cuh"
 #include "rows.cuh"
 
@@ -39,7 +41,8 @@ __device__ __forceinline__ float4 operator*(const float4& a, float s) {
 __device__ __forceinline__ float4 fma4(const float4& a, const float4& b, const float4& c) {
   return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// sigmoid from the two MUFU approximations (ex2, rcp; ~2 ulp each): 4 instructions instead of an IEEE division
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.0f + exp2_ftz(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float4 sigmoid4(const float4& q) {
   return make_float4(sigmoid_f(q.x), sigmoid_f(q.y), sigmoid_f(q.z), sigmoid_f(q.w));
 }
@@ -61,7 +64,7 @@ __device__ __forceinline__ void load_edges(const VecLayerArgs& a, long long BC, 
     if (SCALAR) {
       S[k] = f4(a.e_scalar[k * BC + r]);
     } else {
-      S[k] = sigmoid4(ld4(a.q_in + (k * BC + r) * a.D + col));
+      S[k] = sigmoid4(ld4(a.q_in + (r * 4 + k) * a.D + col));
     }
     E[k] = S[k] * a.en[k];
   }
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(D / 4) vec_layer_fwd_kernel(const VecLayerArgs
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 base = col < H ? (k < 2 ? fu_mt : fu_mi) : ((k & 1) ? v_ei : v_et);
-          st_planes4(a.m_hi, a.m_lo, (k * BC + r) * D + col, base + E[k]);
+          st_planes4(a.m_hi, a.m_lo, (r * 4 + k) * D + col, base + E[k]);
         }
       }
     }
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(D / 4) vec_layer_fwd_kernel(const VecLayerArgs
 // GEMMs), dfu / dfv planes, dq of the PREVIOUS layer's edge outputs (vector edges in), column partials.
 // ---------------------------------------------------------------------------------------------
 template <int D, bool FULL, bool DYN, bool SCALAR>
-__global__ void __launch_bounds__(D / 4) vec_layer_bwd_kernel(const VecLayerArgs a) {
+__global__ void __launch_bounds__(D / 4, (DYN && SCALAR) ? 4 : 3) vec_layer_bwd_kernel(const VecLayerArgs a) {
   constexpr int H = D / 2;
   const int col = threadIdx.x * 4;
   const long long B = a.B, C = a.C, BC = B * C;
@@ -136,65 +139,77 @@ __global__ void __launch_bounds__(D / 4) vec_layer_bwd_kernel(const VecLayerArgs
   const float inv_c = 1.0f / (float)a.C;
   float4 p_bm = f4(0.f);        // sum of dq over this CTA's rows: b_m gradient of the previous layer
   float4 p_uv = f4(0.f);        // columns < H: b_u gradient, columns >= H: b_v gradient
+  // (measured: __restrict__ copies of the pointers let the compiler hoist the next candidate's loads, which costs
+  // 24 registers and two resident CTAs per SM -- slower; occupancy, not load hoisting, feeds HBM here)
+  const float* xa = a.xa;
+  const float* dz = a.dz;
+  const float* q_in = a.q_in;
+  const float* e_scalar = a.e_scalar;
+  const float* dm = a.dm;
+  float* dxa = a.dxa;
+  bf16* dq_hi = a.dq_hi;
+  bf16* dq_lo = a.dq_lo;
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-    const float4 mt = ld4(a.xa + b * D + col);
-    const float4 mi = ld4(a.xa + (B + b) * D + col);
-    const float4 dzmt = ld4(a.dz + b * D + col);
-    const float4 dzmi = FULL ? ld4(a.dz + (B + b) * D + col) : f4(0.f);
+    const float4 mt = ld4(xa + b * D + col);
+    const float4 mi = ld4(xa + (B + b) * D + col);
+    const float4 dzmt = ld4(dz + b * D + col);
+    const float4 dzmi = FULL ? ld4(dz + (B + b) * D + col) : f4(0.f);
     const float4 smt = dzmt * inv_c, smi = dzmi * inv_c;
     float4 dmt = dzmt, dmi = dzmi;
     float4 dfu_mt = f4(0.f), dfu_mi = f4(0.f);
     for (long long c = 0; c < C; ++c) {
       const long long r = b * C + c;
-      const float4 et = ld4(a.xa + (2 * B + r) * D + col);
-      const float4 ei = ld4(a.xa + (2 * B + BC + r) * D + col);
-      float4 E[4], S[4];
-      load_edges<SCALAR>(a, BC, r, col, E, S);
-      const float4 dzet = ld4(a.dz + (row_et + r) * D + col);
-      const float4 dzei = FULL ? ld4(a.dz + (2 * B + BC + r) * D + col) : f4(0.f);
-      st4(a.dxa + (2 * B + r) * D + col, fma4(smt, E[0], fma4(smi, E[2], dzet)));
-      st4(a.dxa + (2 * B + BC + r) * D + col, fma4(smt, E[1], fma4(smi, E[3], dzei)));
-      dmt = fma4(dzet, E[0], fma4(dzei, E[1], dmt));
-      dmi = fma4(dzet, E[2], fma4(dzei, E[3], dmi));
-      if (DYN || !SCALAR) {
-        float4 dE[4];
-        dE[0] = fma4(smt, et, dzet * mt);
-        dE[1] = fma4(smt, ei, dzei * mt);
-        dE[2] = fma4(smi, et, dzet * mi);
-        dE[3] = fma4(smi, ei, dzei * mi);
-        if (DYN) {
-          float4 dfv_et = f4(0.f), dfv_ei = f4(0.f);
+      const float4 et = ld4(xa + (2 * B + r) * D + col);
+      const float4 ei = ld4(xa + (2 * B + BC + r) * D + col);
+      const float4 dzet = ld4(dz + (row_et + r) * D + col);
+      const float4 dzei = FULL ? ld4(dz + (2 * B + BC + r) * D + col) : f4(0.f);
+      float4 det = dzet, dei = dzei;
+      float4 dfv_et = f4(0.f), dfv_ei = f4(0.f);
+      // one edge type at a time (k = 2 u + v: u = mt | mi, v = et | ei) keeps a single edge vector live:
+      //   forward   a_u += E_k x_v / C,  a_v += E_k m_u
+      //   backward  dx_v += (dz_u / C) E_k,  dm_u += dz_v E_k,  dE_k = (dz_u / C) x_v + dz_v m_u
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 dmk = ld4(a.dm + (k * BC + r) * D + col);
-            dE[k] = dE[k] + dmk;
+      for (int k = 0; k < 4; ++k) {
+        const float4& s_u = k < 2 ? smt : smi;
+        const float4& m_u = k < 2 ? mt : mi;
+        const float4& x_v = (k & 1) ? ei : et;
+        const float4& dz_v = (k & 1) ? dzei : dzet;
+        float4 S;
+        if (SCALAR) S = f4(e_scalar[k * BC + r]);
+        else S = sigmoid4(ld4(q_in + (r * 4 + k) * D + col));
+        const float4 E = S * a.en[k];
+        if (k & 1) dei = fma4(s_u, E, dei); else det = fma4(s_u, E, det);
+        if (k < 2) dmt = fma4(dz_v, E, dmt); else dmi = fma4(dz_v, E, dmi);
+        if (DYN || !SCALAR) {
+          float4 dE = fma4(s_u, x_v, dz_v * m_u);
+          if (DYN) {
+            const float4 dmk = ld4(dm + (r * 4 + k) * D + col);
+            dE = dE + dmk;
             if (col < H) {
               if (k < 2) dfu_mt = dfu_mt + dmk; else dfu_mi = dfu_mi + dmk;
             } else {
               if (k & 1) dfv_ei = dfv_ei + dmk; else dfv_et = dfv_et + dmk;
             }
           }
-          if (col >= H) {
-            st_planes4(a.dfv_hi, a.dfv_lo, r * H + (col - H), dfv_et);
-            st_planes4(a.dfv_hi, a.dfv_lo, (BC + r) * H + (col - H), dfv_ei);
-            p_uv = p_uv + dfv_et + dfv_ei;
-          }
-        }
-        if (!SCALAR) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          if (!SCALAR) {
             // E_k = en_k * S_k, S_k = sigmoid(q_k):  dq_k = dE_k * en_k * S_k * (1 - S_k)
-            const float4 ds = make_float4(S[k].x * (1.f - S[k].x), S[k].y * (1.f - S[k].y), S[k].z * (1.f - S[k].z),
-                                          S[k].w * (1.f - S[k].w));
-            const float4 dq = dE[k] * ds * a.en[k];
-            st_planes4(a.dq_hi, a.dq_lo, (k * BC + r) * D + col, dq);
+            const float4 ds = make_float4(S.x * (1.f - S.x), S.y * (1.f - S.y), S.z * (1.f - S.z), S.w * (1.f - S.w));
+            const float4 dq = dE * ds * a.en[k];
+            st_planes4(dq_hi, dq_lo, (r * 4 + k) * D + col, dq);
             p_bm = p_bm + dq;
           }
         }
       }
+      st4(dxa + (2 * B + r) * D + col, det);
+      st4(dxa + (2 * B + BC + r) * D + col, dei);
+      if (DYN && col >= H) {
+        st_planes4(a.dfv_hi, a.dfv_lo, r * H + (col - H), dfv_et);
+        st_planes4(a.dfv_hi, a.dfv_lo, (BC + r) * H + (col - H), dfv_ei);
+        p_uv = p_uv + dfv_et + dfv_ei;
+      }
     }
-    st4(a.dxa + b * D + col, dmt);
-    st4(a.dxa + (B + b) * D + col, dmi);
+    st4(dxa + b * D + col, dmt);
+    st4(dxa + (B + b) * D + col, dmi);
     if (DYN && col < H) {
       st_planes4(a.dfu_hi, a.dfu_lo, b * H + col, dfu_mt);
       st_planes4(a.dfu_hi, a.dfu_lo, (B + b) * H + col, dfu_mi);
@@ -308,30 +323,39 @@ int vec_rows_bwd(cudaStream_t stream, const VecRowsBwdArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// strided_colsum: out[i] = sum_{c < count} src[c * stride + i], i < n   (fixed order: bit-reproducible)
+// strided_colsum_multi: out[i] = sum_{c < count} src[c * stride + i], i < n, for every queued job in ONE launch
+// (blockIdx.y = job).  32 columns x 32 CTA-slices per block, fixed summation order: bit-reproducible.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) strided_colsum_kernel(const float* __restrict__ src, int count, long long stride,
-                                                             int n, float* __restrict__ out) {
-  __shared__ float red[8][33];
+__global__ void __launch_bounds__(1024) strided_colsum_multi_kernel(const StridedColsumJobs jobs) {
+  __shared__ float red[32][33];
+  const StridedColsumJob j = jobs.job[blockIdx.y];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   float t = 0.f;
-  if (i < n)
-    for (int c = slice; c < count; c += 8) t += src[(long long)c * stride + i];
+  if (i < j.n) {
+#pragma unroll 4
+    for (int c = slice; c < j.count; c += 32) t += j.src[(long long)c * j.stride + i];
+  }
   red[slice][lane] = t;
   __syncthreads();
-  if (slice == 0 && i < n) {
+  if (slice == 0 && i < j.n) {
     float r = 0.f;
 #pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2) r += red[s2][lane];
-    out[i] = r;
+    for (int s2 = 0; s2 < 32; ++s2) r += red[s2][lane];
+    j.out[i] = r;
   }
 }
 
-int strided_colsum(cudaStream_t stream, const float* src, int count, long long stride, int n, float* out) {
+int strided_colsum_multi(cudaStream_t stream, const StridedColsumJobs& jobs) {
+  if (jobs.count <= 0) return DRIN_OK;
   prof::Scope prof_scope(stream, prof::GCN_BWD);
-  if (!src || !out || n <= 0 || count <= 0) return fail(DRIN_ERR_ARG, "strided_colsum: bad argument");
-  strided_colsum_kernel<<<(n + 31) / 32, 256, 0, stream>>>(src, count, stride, n, out);
+  int nmax = 0;
+  for (int k = 0; k < jobs.count; ++k) {
+    const StridedColsumJob& j = jobs.job[k];
+    if (!j.src || !j.out || j.n <= 0 || j.count <= 0) return fail(DRIN_ERR_ARG, "strided_colsum_multi: bad job %d", k);
+    nmax = j.n > nmax ? j.n : nmax;
+  }
+  strided_colsum_multi_kernel<<<dim3((nmax + 31) / 32, jobs.count), 1024, 0, stream>>>(jobs);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }

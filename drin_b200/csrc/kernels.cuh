@@ -175,7 +175,8 @@ struct VecLayerArgs {
   float en[4];                // gcn_edge_enabled (model.py:122)
   const float* xa;            // [2B+2BC, D] activated vertices entering the layer (mt, mi, et, ei)
   const float* e_scalar;      // [4, BC] scalar input edges (first layer), or null:
-  const float* q_in;          // [4BC, D] PRE-sigmoid vector edges produced by the previous layer
+  const float* q_in;          // [4BC, D] PRE-sigmoid vector edges produced by the previous layer; this and every other
+                              // [4BC, D] matrix below is candidate-major: row r * 4 + k (candidate r, edge type k)
   // forward
   const float* fu;            // [2B, D/2]  W_u xm + b_u   (dyn)
   const float* fv;            // [2BC, D/2] W_v xv + b_v   (dyn; et rows, then ei rows)
@@ -205,7 +206,24 @@ struct VecRowsBwdArgs {
 };
 int vec_rows_bwd(cudaStream_t stream, const VecRowsBwdArgs& a);
 int vec_rows_ctas();
-int strided_colsum(cudaStream_t stream, const float* src, int count, long long stride, int n, float* out);
+// column sums of the per-CTA partials above; every job of a backward pass is reduced by ONE launch at its end
+struct StridedColsumJob {
+  const float* src;
+  float* out;
+  long long stride;           // floats between consecutive partial rows
+  int count, n;               // partial rows, columns
+};
+struct StridedColsumJobs {
+  static constexpr int MAX = 7 * DRIN_MAX_LAYERS;
+  StridedColsumJob job[MAX];
+  int count = 0;
+  int add(const float* src, int cnt, long long stride, int n, float* out) {
+    if (count >= MAX) return 1;
+    job[count++] = StridedColsumJob{src, out, stride, cnt, n};
+    return 0;
+  }
+};
+int strided_colsum_multi(cudaStream_t stream, const StridedColsumJobs& jobs);
 
 // loss.cu
 size_t triplet_scratch_bytes(int B, int C);

@@ -275,7 +275,7 @@ def test_vector_edge_forward_stage_by_stage(dataset, B, cands, layers, mask, kw)
         if l < layers - 1:
             want = torch.cat([Vn[0], Vn[1], Vn[2].flatten(0, 1), Vn[3].flatten(0, 1)])
             q = eng.debug_buffer(ctx, "q", l).cpu()
-            got_e = torch.sigmoid(q).view(4, B, cands + 1, 768)
+            got_e = torch.sigmoid(q).view(B, cands + 1, 4, 768).permute(2, 0, 1, 3)   # rows are candidate-major (r * 4 + k)
             assert rel_err(got_e, torch.stack(En)) < 2e-5, l
         else:
             want = torch.cat([Vn[0], Vn[2].flatten(0, 1)])
