@@ -67,8 +67,9 @@ def algorithmic_bytes_per_mention(C, wm, D=768, R=2048, P=49, Om=3, Oe=1, Le=64,
 
 def gemm_flops_per_mention(C, train, D=768, R=2048, vector=False):
     u, r = 2 * D * D, 2 * R * D
-    if vector:   # per unit: projections u + r; layer 1: W_h 2u, W_u | W_v (D -> D/2) on both kinds u, W_m on 4 edges 4u;
-        return (1 + C) * ((2 * r + 26 * u) if train else (r + 9 * u))   # layer 2: W_h on the text kind u
+    if vector:   # as the reference formulates it, per unit: projections u + r; layer 1: W_h 2u, W_u | W_v (D -> D/2) on both
+        # kinds u, W_m on the 4 edge types 4u; layer 2: W_h on the text kind u
+        return (1 + C) * ((2 * r + 26 * u) if train else (r + 9 * u))
     return (1 + C) * ((2 * r + 17 * u) if train else (r + 6 * u))     # reference-necessary
 
 

@@ -134,6 +134,7 @@ int drin_debug_option(const char* name, int32_t value) {
   else if (!strcmp(name, "layer_fwd_variant")) debug_set_layer_fwd_variant(value);
   else if (!strcmp(name, "layer_bwd_variant")) debug_set_layer_bwd_variant(value);
   else if (!strcmp(name, "defer_reductions")) debug_set_defer_reductions(value);
+  else if (!strcmp(name, "vec_bwd_width")) debug_set_vec_bwd_width(value);
   else return fail(DRIN_ERR_ARG, "drin_debug_option: unknown option '%s'", name);
   return DRIN_OK;
 }
@@ -155,6 +156,9 @@ int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name,
   else if (!strcmp(name, "xa")) { *ptr = lw.xa; *rows = 2 * B + 2 * BC; *cols = D; }
   else if (!strcmp(name, "fv")) { *ptr = lw.fv; *rows = 2 * BC; *cols = D / 2; }
   else if (!strcmp(name, "q")) { *ptr = lw.q; *rows = 4 * BC; *cols = D; }
+  else if (!strcmp(name, "edge_a")) { *ptr = lw.edge_a; *rows = 2 * B; *cols = D; }
+  else if (!strcmp(name, "edge_bv")) { *ptr = lw.edge_bv; *rows = 2 * BC; *cols = D; }
+  else if (!strcmp(name, "edge_w1")) { *ptr = lw.edge_w1; *rows = 1; *cols = D; }
   else if (!strcmp(name, "g")) { *ptr = lw.g; *rows = 2 * B; *cols = D; }
   else if (!strcmp(name, "edges_out")) { *ptr = lw.edges_out; *rows = 4; *cols = BC; }
   else if (!strcmp(name, "dz")) { *ptr = ws.dz; *rows = 2 * B + 2 * BC; *cols = D; }

@@ -62,7 +62,14 @@ static int plan_vector(const drin_config& c, Bump& m, Workspace& ws) {
       if (lw.dyn) lw.xa_p = m.planes(rows_all * D, split);
     }
     lw.xm = lw.xa;
-    if (lw.dyn) {
+    lw.affine = lw.dyn && l == 0;
+    if (lw.affine) {
+      lw.fu_p = m.planes(2 * B * H, split);
+      lw.fv_p = m.planes(2 * BC * H, split);
+      lw.edge_a = m.take<float>(2 * B * D);
+      lw.edge_bv = m.take<float>(2 * BC * D);
+      lw.edge_w1 = m.take<float>(D);
+    } else if (lw.dyn) {
       lw.fu = m.take<float>(2 * B * H);
       lw.fv = m.take<float>(2 * BC * H);
       lw.m_p = m.planes(4 * BC * D, split);
@@ -76,10 +83,17 @@ static int plan_vector(const drin_config& c, Bump& m, Workspace& ws) {
     ws.dz = m.take<float>(rows_all * D);
     ws.dxa = m.take<float>(rows_all * D);
     ws.dxuv = m.take<float>(rows_all * D);
-    ws.dm = m.take<float>(4 * BC * D);
-    ws.dq_p = m.planes(4 * BC * D, split);
+    if (L > 2) {            // general edge updates exist only above the first layer
+      ws.dm = m.take<float>(4 * BC * D);
+      ws.dq_p = m.planes(4 * BC * D, split);
+    }
     ws.dfu_p = m.planes(2 * B * H, split);
     ws.dfv_p = m.planes(2 * BC * H, split);
+    ws.da_p = m.planes(2 * B * D, split);
+    ws.dbv_p = m.planes(2 * BC * D, split);
+    ws.dwm_a = m.take<float>(D * H);
+    ws.dwm_b = m.take<float>(D * H);
+    ws.dw1 = m.take<float>(D);
     ws.dx0 = m.planes(rows_all * D, split);
     if (ws.slices > 1) {
       ws.slice_part = m.take<float>(B * ws.slices * 4 * D);
@@ -91,7 +105,7 @@ static int plan_vector(const drin_config& c, Bump& m, Workspace& ws) {
     ws.colsum_ctas = backward_ctas();
     ws.colsum_floats = (size_t)2 * ws.colsum_ctas * 3 * D;        // score_bwd (and its sliced mention finish)
     ws.colsum = m.take<float>(ws.colsum_floats);
-    ws.vec_part = m.take<float>((size_t)L * vec_layer_ctas() * 2 * D);
+    ws.vec_part = m.take<float>((size_t)L * vec_layer_ctas() * 3 * D);
     ws.rows_part = m.take<float>((size_t)L * vec_rows_ctas() * 4 * D);
   }
   ws.bytes = align_up(m.off, 256);
@@ -196,6 +210,18 @@ static Operand op(const Planes& p, long long rows, int cols, long long row_offse
   return o;
 }
 
+// W_m[:, :H] (half = 0) or W_m[:, H:] (half = 1) as a [D, H] operand inside the [D, D] planes (leading dimension D)
+static Operand wm_half(const Planes& w_m, int D, int half) {
+  Operand o;
+  const int H = D / 2;
+  o.hi = w_m.hi + half * H;
+  o.lo = w_m.lo ? w_m.lo + half * H : nullptr;
+  o.rows = D;
+  o.cols = H;
+  o.ld = D;
+  return o;
+}
+
 // GCN layers + scoring with vector edges (drin/model.py:205-209 with gcn_edge_feature == "vector").
 static int forward_vector_layers(const drin_config& c, const drin_params& p, Workspace& ws, float* scores,
                                  cudaStream_t stream) {
@@ -214,26 +240,41 @@ static int forward_vector_layers(const drin_config& c, const drin_params& p, Wor
       const drin_layer_params& pp = p.layer[l - 1];
       DRIN_TRY(mention_ln(stream, D, pw.h, 2 * B + 2 * BC, pp.ln_w, pp.ln_b, lw.xa, lw.dyn ? lw.xa_p.hi : nullptr,
                           lw.dyn ? lw.xa_p.lo : nullptr));
-      va.q_in = pw.q;
+      if (pw.affine) {
+        va.e_scalar = ws.edges0; va.edge_a = pw.edge_a; va.edge_bv = pw.edge_bv; va.edge_w1 = pw.edge_w1;
+      } else {
+        va.q_in = pw.q;
+      }
     }
     va.xa = lw.xa;
+    va.dyn = lw.dyn && !lw.affine;
     if (lw.dyn) {
       // model.py:149: fu = W_u u for the 2B mention vertices, fv = W_v v for the 2BC candidate vertices (D -> D/2)
       GemmEpilogue ep;
-      ep.ldc = H;
-      ep.C = lw.fu; ep.bias = lp.b_u;
+      ep.ldc = H; ep.ld_planes = H;
+      ep.C = lw.fu; ep.bias = lp.b_u; ep.out_hi = lw.fu_p.hi; ep.out_lo = lw.fu_p.lo;     // affine: planes, else fp32
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.xa_p, 2 * B, D), op(lw.w_u, H, D), 2 * B, H, D, ep));
-      ep.C = lw.fv; ep.bias = lp.b_v;
+      ep.C = lw.fv; ep.bias = lp.b_v; ep.out_hi = lw.fv_p.hi; ep.out_lo = lw.fv_p.lo;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.xa_p, 2 * BC, D, 2 * B), op(lw.w_v, H, D), 2 * BC, H, D, ep));
-      va.fu = lw.fu; va.fv = lw.fv;
-      va.m_hi = lw.m_p.hi; va.m_lo = lw.m_p.lo;
+      if (lw.affine) {
+        // first layer: W_m(cat[fu, fv] + e 1) + b_m = (fu W_m[:, :H]^T + b_m) + fv W_m[:, H:]^T + e (W_m 1); nothing per edge type
+        GemmEpilogue ea;
+        ea.ldc = D; ea.C = lw.edge_a; ea.bias = lp.b_m;
+        DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.fu_p, 2 * B, H), wm_half(lw.w_m, D, 0), 2 * B, D, H, ea));
+        ea.C = lw.edge_bv; ea.bias = nullptr;
+        DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.fv_p, 2 * BC, H), wm_half(lw.w_m, D, 1), 2 * BC, D, H, ea));
+        DRIN_TRY(rowsum(stream, lp.w_m, D, D, lw.edge_w1));
+      } else {
+        va.fu = lw.fu; va.fv = lw.fv;
+        va.m_hi = lw.m_p.hi; va.m_lo = lw.m_p.lo;
+      }
     }
     va.z_hi = lw.z.hi; va.z_lo = lw.z.lo;
     DRIN_TRY(vec_layer_fwd(stream, va));
     GemmEpilogue eh;
     eh.ldc = D; eh.C = lw.h; eh.bias = lp.b_h;
     DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.z, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, eh));
-    if (lw.dyn) {   // model.py:133: q = W_m(cat[fu, fv] + e) + b_m for the four edge types at once; sigmoid in the consumer
+    if (va.dyn) {   // model.py:133: q = W_m(cat[fu, fv] + e) + b_m for the four edge types at once; sigmoid in the consumer
       GemmEpilogue em;
       em.ldc = D; em.C = lw.q; em.bias = lp.b_m;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.m_p, 4 * BC, D), op(lw.w_m, D, D), 4 * BC, D, D, em));

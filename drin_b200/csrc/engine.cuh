@@ -29,8 +29,14 @@ struct LayerWs {
   float* xa = nullptr;         // [2B+2BC, D] activated vertices entering this layer (layer 0: alias of x0)
   Planes xa_p;                 // planes of xa (dyn: A operand of the W_u / W_v GEMMs)
   float* fv = nullptr;         // [2BC, D/2] W_v xv + b_v (dyn); fu above is [2B, D/2]
-  Planes m_p;                  // [4BC, D] cat[fu, fv] + E_k (dyn): A operand of the W_m GEMM
-  float* q = nullptr;          // [4BC, D] pre-sigmoid edge outputs W_m m + b_m (dyn)
+  Planes m_p;                  // [4BC, D] cat[fu, fv] + E_k (dyn, not the first layer): A operand of the W_m GEMM
+  float* q = nullptr;          // [4BC, D] pre-sigmoid edge outputs W_m m + b_m (dyn, not the first layer)
+  // first layer of the vector path (its own edges are scalars): edge outputs in affine form, see gcn_vec.cu
+  bool affine = false;
+  Planes fv_p;                 // [2BC, D/2] planes of fv (fu_p above: [2B, D/2])
+  float* edge_a = nullptr;     // [2B, D]  fu W_m[:, :H]^T + b_m
+  float* edge_bv = nullptr;    // [2BC, D] fv W_m[:, H:]^T
+  float* edge_w1 = nullptr;    // [D]      W_m 1
 };
 
 struct Workspace {
@@ -71,7 +77,12 @@ struct Workspace {
   float* dm = nullptr;               // [4BC, D] gradient w.r.t. m
   Planes dq_p;                       // [4BC, D] gradient w.r.t. the pre-sigmoid edge outputs of the layer below
   Planes dfv_p;                      // [2BC, D/2]; dfu_p above is [2B, D/2]
-  float* vec_part = nullptr;         // [L][vec_layer_ctas()][2][D] column partials of vec_layer_bwd (one region per layer:
+  Planes da_p;                       // [2B, D]  gradient w.r.t. edge_a of the first layer
+  Planes dbv_p;                      // [2BC, D] gradient w.r.t. edge_bv of the first layer
+  float* dwm_a = nullptr;            // [D, D/2] dW_m[:, :H] of the first layer (assembled by wm_fixup)
+  float* dwm_b = nullptr;            // [D, D/2] dW_m[:, H:]
+  float* dw1 = nullptr;              // [D]      gradient w.r.t. edge_w1
+  float* vec_part = nullptr;         // [L][vec_layer_ctas()][3][D] column partials of vec_layer_bwd (one region per layer:
   float* rows_part = nullptr;        // [L][vec_rows_ctas()][4][D]  ... of vec_rows_bwd       all reduced by one launch)
 };
 

@@ -59,6 +59,18 @@ static int weight_grad(cudaStream_t s, const Workspace& ws, Deferred& df, const 
   return gemm_tcgen05(s, GEMM_TN, A, B, M, N, K, ep, ksplit, region, g_defer_reductions ? &df.splitk : nullptr);
 }
 
+// W_m[:, :H] / W_m[:, H:] as the [K = D, N = H] operand of an NN GEMM (dA W_m[:, :H], dBv W_m[:, H:])
+static Operand wm_half_kn(const Planes& w_m, int D, int half) {
+  Operand o;
+  const int H = D / 2;
+  o.hi = w_m.hi + half * H;
+  o.lo = w_m.lo ? w_m.lo + half * H : nullptr;
+  o.rows = D;
+  o.cols = H;
+  o.ld = D;
+  return o;
+}
+
 // Backward of the vector-edge layers (forward_vector_layers in engine.cu), layer by layer from the scores down:
 //   dZ = dH W_h, dW_h = dH^T Z;  [edge update] dM = dQ W_m, dW_m = dQ^T M;  vec_layer_bwd (messages, sigmoid, cat);
 //   [edge update] dW_u = dFu^T Xm, dW_v = dFv^T Xv, dX += dFu W_u | dFv W_v;  vec_rows_bwd (GELU + LayerNorm).
@@ -97,32 +109,58 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dh, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, ez));
       DRIN_TRY(weight_grad(stream, ws, df, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
     }
-    if (lw.dyn) {     // dq_p holds the gradient w.r.t. this layer's pre-sigmoid edge outputs (written by layer l + 1)
+    const bool general = lw.dyn && !lw.affine;
+    if (general) {     // dq_p holds the gradient w.r.t. this layer's pre-sigmoid edge outputs (written by layer l + 1)
       GemmEpilogue em;
       em.C = ws.dm; em.ldc = D;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dq_p, 4 * BC, D), op(lw.w_m, D, D), 4 * BC, D, D, em));
       DRIN_TRY(weight_grad(stream, ws, df, op(ws.dq_p, 4 * BC, D), op(lw.m_p, 4 * BC, D), D, D, 4 * BC, lg.w_m));
     }
     VecLayerArgs va{};
-    va.B = c.batch; va.C = c.candidates; va.D = D; va.full = lw.full; va.dyn = lw.dyn;
+    va.B = c.batch; va.C = c.candidates; va.D = D; va.full = lw.full; va.dyn = general;
     for (int k = 0; k < 4; ++k) va.en[k] = c.edge_enabled[k];
     va.xa = lw.xa;
-    if (l == 0) va.e_scalar = ws.edges0; else va.q_in = ws.layer[l - 1].q;
+    if (l == 0) {
+      va.e_scalar = ws.edges0;
+    } else if (ws.layer[l - 1].affine) {       // the layer below is the first layer: its edge outputs are A_u + Bv_v + e w1
+      const LayerWs& pw = ws.layer[l - 1];
+      va.e_scalar = ws.edges0; va.edge_a = pw.edge_a; va.edge_bv = pw.edge_bv; va.edge_w1 = pw.edge_w1;
+      va.da_hi = ws.da_p.hi; va.da_lo = ws.da_p.lo;
+      va.dbv_hi = ws.dbv_p.hi; va.dbv_lo = ws.dbv_p.lo;
+    } else {
+      va.q_in = ws.layer[l - 1].q;
+      va.dq_hi = ws.dq_p.hi; va.dq_lo = ws.dq_p.lo;      // safe: dm / dW_m above already consumed dq_p
+    }
     va.dz = ws.dz;
     va.dxa = ws.dxa;
-    if (lw.dyn) {
+    if (general) {
       va.dm = ws.dm;
       va.dfu_hi = ws.dfu_p.hi; va.dfu_lo = ws.dfu_p.lo;
       va.dfv_hi = ws.dfv_p.hi; va.dfv_lo = ws.dfv_p.lo;
     }
-    if (l > 0) { va.dq_hi = ws.dq_p.hi; va.dq_lo = ws.dq_p.lo; }      // safe: dm / dW_m above already consumed dq_p
     va.partials = vec_part;
     int prow = 0;
     DRIN_TRY(vec_layer_bwd(stream, va, &prow));
-    if (l > 0) DRIN_TRY(colsum(vec_part, prow, 2 * D, D, grads.layer[l - 1].b_m));
+    if (l > 0) {
+      DRIN_TRY(colsum(vec_part, prow, 3 * D, D, grads.layer[l - 1].b_m));
+      if (ws.layer[l - 1].affine) DRIN_TRY(colsum(vec_part + 2 * D, prow, 3 * D, D, ws.dw1));
+    }
+    if (general) {
+      DRIN_TRY(colsum(vec_part + D, prow, 3 * D, H, lg.b_u));
+      DRIN_TRY(colsum(vec_part + D + H, prow, 3 * D, H, lg.b_v));
+    }
+    if (lw.affine) {
+      // first layer: dA, dBv (written by the layer above) -> dFu, dFv and the two halves of dW_m; no per-edge-type GEMM
+      GemmEpilogue ef;
+      ef.ld_planes = H;
+      ef.out_hi = ws.dfu_p.hi; ef.out_lo = ws.dfu_p.lo;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.da_p, 2 * B, D), wm_half_kn(lw.w_m, D, 0), 2 * B, H, D, ef));
+      ef.out_hi = ws.dfv_p.hi; ef.out_lo = ws.dfv_p.lo;
+      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dbv_p, 2 * BC, D), wm_half_kn(lw.w_m, D, 1), 2 * BC, H, D, ef));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.da_p, 2 * B, D), op(lw.fu_p, 2 * B, H), D, H, 2 * B, ws.dwm_a));
+      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dbv_p, 2 * BC, D), op(lw.fv_p, 2 * BC, H), D, H, 2 * BC, ws.dwm_b));
+    }
     if (lw.dyn) {
-      DRIN_TRY(colsum(vec_part + D, prow, 2 * D, H, lg.b_u));
-      DRIN_TRY(colsum(vec_part + D + H, prow, 2 * D, H, lg.b_v));
       DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfu_p, 2 * B, H), op(lw.xa_p, 2 * B, D), H, D, 2 * B, lg.w_u));
       DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfv_p, 2 * BC, H), op(lw.xa_p, 2 * BC, D, 2 * B), H, D, 2 * BC, lg.w_v));
       GemmEpilogue ex;
@@ -155,7 +193,15 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
       DRIN_TRY(colsum(rows_part + 3 * D, vec_rows_ctas(), pstride, D, grads.b_ei));
     }
   }
-  return strided_colsum_multi(stream, cs);
+  DRIN_TRY(strided_colsum_multi(stream, cs));
+  if (ws.layer[0].affine) {
+    // dW_m, b_u, b_v of the first layer need the finished split-K sums and column sums: reduce what is queued, then assemble
+    DRIN_TRY(splitk_reduce_multi(stream, df.splitk));
+    df.splitk.count = 0;
+    const drin_layer_params& g0 = grads.layer[0];
+    DRIN_TRY(wm_fixup(stream, ws.dwm_a, ws.dwm_b, ws.dw1, g0.b_m, p.layer[0].w_m, D, g0.w_m, g0.b_u, g0.b_v));
+  }
+  return DRIN_OK;
 }
 
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,

@@ -174,9 +174,13 @@ struct VecLayerArgs {
   bool dyn;                   // this layer runs the dynamic edge update (full layers of a dynamic-edge model)
   float en[4];                // gcn_edge_enabled (model.py:122)
   const float* xa;            // [2B+2BC, D] activated vertices entering the layer (mt, mi, et, ei)
-  const float* e_scalar;      // [4, BC] scalar input edges (first layer), or null:
-  const float* q_in;          // [4BC, D] PRE-sigmoid vector edges produced by the previous layer; this and every other
-                              // [4BC, D] matrix below is candidate-major: row r * 4 + k (candidate r, edge type k)
+  // edge input, one of three forms (gcn_vec.cu: EdgeMode)
+  const float* e_scalar;      // [4, BC] scalar input edges: the edges of a FIRST layer (SCALAR; also read by AFFINE)
+  const float* q_in;          // [4BC, D] PRE-sigmoid vector edges produced by the previous layer (VECTOR); this and every
+                              // other [4BC, D] matrix below is candidate-major: row r * 4 + k (candidate r, edge type k)
+  const float* edge_a;        // AFFINE (the previous layer was a first layer): q_k[r] = edge_a[u_k B + b] + edge_bv[v_k BC + r]
+  const float* edge_bv;       //   + en_k e_scalar[k, r] edge_w1;  edge_a [2B, D] = fu W_m[:, :H]^T + b_m, edge_bv [2BC, D] =
+  const float* edge_w1;       //   fv W_m[:, H:]^T, edge_w1 [D] = W_m 1
   // forward
   const float* fu;            // [2B, D/2]  W_u xm + b_u   (dyn)
   const float* fv;            // [2BC, D/2] W_v xv + b_v   (dyn; et rows, then ei rows)
@@ -188,9 +192,16 @@ struct VecLayerArgs {
   float* dxa;                 // [2B+2BC, D] gradient w.r.t. xa (message paths only; W_u / W_v paths are GEMMs)
   bf16* dfu_hi; bf16* dfu_lo; // [2B, D/2]  (dyn)
   bf16* dfv_hi; bf16* dfv_lo; // [2BC, D/2] (dyn)
-  bf16* dq_hi; bf16* dq_lo;   // [4BC, D] gradient w.r.t. q_in (vector edges in)
-  float* partials;            // [ctas][2][D]: sum dq (b_m gradient of the previous layer); [b_u | b_v] gradient
+  bf16* dq_hi; bf16* dq_lo;   // [4BC, D] gradient w.r.t. q_in (VECTOR)
+  bf16* da_hi; bf16* da_lo;   // [2B, D]  gradient w.r.t. edge_a  (AFFINE)
+  bf16* dbv_hi; bf16* dbv_lo; // [2BC, D] gradient w.r.t. edge_bv (AFFINE)
+  float* partials;            // [ctas][3][D]: sum dq (b_m gradient of the previous layer); [b_u | b_v] gradient of this
+                              // layer; sum en_k e_k dq_k (edge_w1 gradient, AFFINE)
 };
+int rowsum(cudaStream_t stream, const float* w, int rows, int cols, float* out);
+int wm_fixup(cudaStream_t stream, const float* dwa, const float* dwb, const float* dw1, const float* db_m,
+             const float* w_m, int D, float* dw_m, float* db_u, float* db_v);
+void debug_set_vec_bwd_width(int v);
 int vec_layer_fwd(cudaStream_t stream, const VecLayerArgs& a);
 int vec_layer_bwd(cudaStream_t stream, const VecLayerArgs& a, int* partial_rows);
 int vec_layer_ctas();

@@ -194,7 +194,8 @@ void drin_profile_enable(int32_t on);
 int drin_profile_collect(double* ms, double* flops, double* bytes, long long* count);
 
 /* Test hook: device pointer / shape of a named fp32 intermediate ("edges0", "x0", "h", "xm", "fu", "g",
- * "edges_out", "dz"; vector edges: "xa", "fv", "q") inside a workspace planned for cfg.  Not part of the drop-in surface. */
+ * "edges_out", "dz"; vector edges: "xa", "fu", "fv", "q", and for the first layer "edge_a", "edge_bv", "edge_w1") inside a
+ * workspace planned for cfg.  Not part of the drop-in surface. */
 int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name, int32_t layer, void** ptr,
                       int64_t* rows, int64_t* cols);
 

@@ -242,6 +242,7 @@ def test_forward_intermediates_stage_by_stage(dataset, B, cands, layers, kw, var
 
 @pytest.mark.parametrize("dataset,B,cands,layers,mask,kw", [
     ("wikidiverse", 9, 10, 2, (1, 1, 1, 1), {}), ("wikidiverse", 5, 10, 3, (1, 0, 1, 1), {}),
+    ("wikidiverse", 4, 6, 4, (1, 1, 0.5, 1), {}),
     ("wikimel", 3, 5, 2, (1, 1, 1, 1), dict(entity_tokens=16, mention_tokens=32))])
 def test_vector_edge_forward_stage_by_stage(dataset, B, cands, layers, mask, kw):
     """gcn_edge_feature="vector" (drin/model.py:112-116,133,139-152): per layer the activated vertices entering it
@@ -263,20 +264,35 @@ def test_vector_edge_forward_stage_by_stage(dataset, B, cands, layers, mask, kw)
         k = O.gcn_keys(l)
         xa = torch.cat([Vl[0], Vl[1], Vl[2].flatten(0, 1), Vl[3].flatten(0, 1)])
         assert rel_err(eng.debug_buffer(ctx, "xa", l).cpu(), xa) < 2e-5, l
+        Vn, En = O.gcn_layer(sd, l, cfg, Vl, El)
         if l < layers - 1:
             fv = torch.cat([F.linear(Vl[2], sd[k["w_v"]], sd[k["b_v"]]).flatten(0, 1),
                             F.linear(Vl[3], sd[k["w_v"]], sd[k["b_v"]]).flatten(0, 1)])
-            assert rel_err(eng.debug_buffer(ctx, "fv", l).cpu(), fv) < 2e-5, l
             fu = torch.cat([F.linear(Vl[0], sd[k["w_u"]], sd[k["b_u"]]), F.linear(Vl[1], sd[k["w_u"]], sd[k["b_u"]])])
-            assert rel_err(eng.debug_buffer(ctx, "fu", l).cpu(), fu) < 2e-5, l
-        Vn, En = O.gcn_layer(sd, l, cfg, Vl, El)
+            Cn = cands + 1
+            if l == 0:
+                # first layer: edge outputs in affine form  q_k = A_u + Bv_v + e_k (W_m 1)  (csrc/gcn_vec.cu header)
+                w_m, b_m = sd[k["w_m"]], sd[k["b_m"]]
+                A = eng.debug_buffer(ctx, "edge_a", l).cpu()
+                Bv = eng.debug_buffer(ctx, "edge_bv", l).cpu()
+                w1 = eng.debug_buffer(ctx, "edge_w1", l).cpu()[0]
+                assert rel_err(A, fu @ w_m[:, :384].t() + b_m) < 2e-5
+                assert rel_err(Bv, fv @ w_m[:, 384:].t()) < 2e-5
+                assert rel_err(w1, w_m.sum(1)) < 1e-6
+                A, Bv = A.view(2, B, 1, 768), Bv.view(2, B, Cn, 768)
+                e_in = torch.stack([e[..., 0] * m for e, m in zip(El, mask)])             # masked scalar input edges
+                got_e = torch.stack([torch.sigmoid(A[kk >> 1] + Bv[kk & 1] + e_in[kk].unsqueeze(-1) * w1)
+                                     for kk in range(4)])
+            else:
+                assert rel_err(eng.debug_buffer(ctx, "fv", l).cpu(), fv) < 2e-5, l
+                assert rel_err(eng.debug_buffer(ctx, "fu", l).cpu(), fu) < 2e-5, l
+                q = eng.debug_buffer(ctx, "q", l).cpu()
+                got_e = torch.sigmoid(q).view(B, Cn, 4, 768).permute(2, 0, 1, 3)   # rows are candidate-major (r * 4 + k)
+            assert rel_err(got_e, torch.stack(En)) < 2e-5, l
         h = eng.debug_buffer(ctx, "h", l).cpu()
         act = F.gelu(F.layer_norm(h, (h.shape[-1],), sd[k["ln_w"]], sd[k["ln_b"]], 1e-5))
         if l < layers - 1:
             want = torch.cat([Vn[0], Vn[1], Vn[2].flatten(0, 1), Vn[3].flatten(0, 1)])
-            q = eng.debug_buffer(ctx, "q", l).cpu()
-            got_e = torch.sigmoid(q).view(B, cands + 1, 4, 768).permute(2, 0, 1, 3)   # rows are candidate-major (r * 4 + k)
-            assert rel_err(got_e, torch.stack(En)) < 2e-5, l
         else:
             want = torch.cat([Vn[0], Vn[2].flatten(0, 1)])
         assert rel_err(act, want) < 2e-5, l

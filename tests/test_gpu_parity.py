@@ -200,3 +200,23 @@ def test_host_feeder_compact_spans_is_bit_identical():
         if compact:
             assert feeder.last_bytes < sum(t.numel() * t.element_size() for t in batch) // 1.5
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["wd_b8_vector", "wd_b6_vector_l3_mask"])
+def test_vector_edge_backward_two_column_variant(name):
+    """The 2-columns-per-thread instantiation of the vector-edge backward kernels (A/B option, csrc/gcn_vec.cu) gives
+    the same gradients as the reference."""
+    path = [p for p in CASES if os.path.basename(p) == name + ".pt"][0]
+    cfg, batch, sd, fx = load_case(path)
+    _option("vec_bwd_width", 2)
+    try:
+        model = _cuda_model(cfg, sd)
+        dbatch = [t.cuda() for t in batch]
+        loss = drin_b200.TripletLoss(cfg.triplet_margin)(dbatch[-1], model(dbatch[:-1]))
+        loss.backward()
+    finally:
+        _option("vec_bwd_width", 0)
+    _, _, grads = O.train_step_grads(sd, batch[:-1], batch[-1], cfg)
+    for key, p in model.named_parameters():
+        if grads[key] is not None:
+            assert rel_err(p.grad.cpu(), grads[key]) < TOL, key
