@@ -6,10 +6,10 @@ Python host side that mirrors the reference's module interface.
 from .model import Model  # noqa: F401
 from .loss import TripletLoss, TopkAccuracy  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from .trainer import GraphedStoreStep, HostFeeder, Trainer  # noqa: F401
+from .trainer import Evaluator, GraphedStoreStep, HostFeeder, Trainer  # noqa: F401
 from .store import FeatureStore, IndexedBatch  # noqa: F401
 
-__all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "GraphedStoreStep", "HostFeeder", "FeatureStore", "IndexedBatch",
+__all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "Evaluator", "GraphedStoreStep", "HostFeeder", "FeatureStore", "IndexedBatch",
            "install_as_reference_module"]
 
 

@@ -124,14 +124,85 @@ class Trainer:
         self.opt.step()
         return loss
 
-    @torch.no_grad()
     def rank_scores(self, batch: Sequence[torch.Tensor], gather: bool = False) -> torch.Tensor:
         """Ranking inference (upstream test_step under no_grad): scores [B_loc, C]; optionally gathered."""
-        m = self.model
-        inputs = batch if hasattr(batch, "mention_index") else tuple(batch[:14])
-        scores, _ = m._engine.forward(inputs, m._param_views(), training=False,
-                                      num_candidates_model=m.num_candidates_model)
-        return gather_rows(scores, self.group) if gather else scores
+        return rank_scores(self.model, batch, self.group, gather)
+
+
+@torch.no_grad()
+def rank_scores(model: Model, batch, group=None, gather: bool = False) -> torch.Tensor:
+    """Forward without backward state over the loader's batch (first 14 tensors) or a ``store.IndexedBatch``."""
+    inputs = batch if hasattr(batch, "mention_index") else tuple(batch[:14])
+    scores, _ = model._engine.forward(inputs, model._param_views(), training=False,
+                                      num_candidates_model=model.num_candidates_model)
+    return gather_rows(scores, group) if gather else scores
+
+
+class Evaluator:
+    """Validation / test loop body of the reference (``MELModel._forward_step`` with type 1 / 2, upstream train.py:30-43)
+    without its per-step host synchronisations: the reference formats ``float(loss)`` and every ``metric.compute()`` into
+    a log line each step and, for ``output_test_result``, copies the scores to the host and writes them out per step
+    (train.py:35-43).  Here the loss sum and the top-k hit counters stay on the device (``drin_topk_hits``), the scores
+    of every step are kept in HBM, and ``compute()`` / ``write_results()`` do ONE device->host read at the end.
+
+    Per-step loss semantics are the reference's: TripletLoss over the batch of that step; ``compute()["loss"]`` is the
+    mean over steps, i.e. what Lightning's epoch aggregation of the returned losses reports."""
+
+    def __init__(self, model: Model, margin: float = 0.25, top_k: Sequence[int] = (1, 3, 5), keep_scores: bool = False):
+        from .loss import TopkAccuracy
+        self.model, self.margin, self.keep_scores = model, float(margin), bool(keep_scores)
+        self.metric = TopkAccuracy(list(top_k), device=model.flat_params.device)
+        self.reset()
+
+    def reset(self) -> None:
+        self.metric.reset()
+        self._loss_sum = torch.zeros(1, dtype=torch.float32, device=self.model.flat_params.device)
+        self._steps = 0
+        self._scores: List[torch.Tensor] = []
+        self._labels: List[torch.Tensor] = []
+
+    @torch.no_grad()
+    def step(self, batch) -> torch.Tensor:
+        """batch: the loader's 15-tuple or a ``store.IndexedBatch``.  Returns the step's loss (device scalar, no sync)."""
+        y = batch.labels if hasattr(batch, "mention_index") else batch[-1]
+        scores = rank_scores(self.model, batch)
+        loss, _ = triplet_loss_sharded(scores, y, self.margin)
+        self._loss_sum += loss
+        self.metric.update(scores, y)
+        self._steps += 1
+        if self.keep_scores:
+            self._scores.append(scores)          # forward() returns a fresh tensor every call
+            self._labels.append(y.to(torch.uint8))
+        return loss.reshape(())
+
+    def compute(self, acc_correction: float = 0.0) -> dict:
+        """One host read.  ``acc_correction``: the reference divides top-k accuracy by ``1 - acc_correction[type]``
+        (train.py:38, args.py:115,123) to discount mentions whose gold entity is not among the candidates."""
+        acc = (self.metric.correct.double() / max(self.metric.total, 1) / (1.0 - acc_correction)).tolist()
+        return {"loss": float(self._loss_sum) / max(self._steps, 1),
+                "topk": {k: a for k, a in zip(self.metric.top_k, acc)}, "mentions": self.metric.total}
+
+    def write_results(self, file, batch_size: Optional[int] = None) -> int:
+        """The reference's ``test-result.txt`` (train.py:40-43): per mention ``"{index}:\t{scores as a list}\n{labels}\n"``
+        with ``index = i + batch_idx * batch_size``.  ``file``: path or text file object.  Returns the mention count."""
+        if not self.keep_scores:
+            raise RuntimeError("Evaluator(keep_scores=True) is needed to write the result file")
+        own = isinstance(file, (str, os.PathLike))
+        fh = open(file, "w") if own else file
+        n = 0
+        try:
+            scores = [s.cpu() for s in self._scores]         # device -> host once, after the loop
+            labels = [y.cpu() for y in self._labels]
+            for batch_idx, (s, y) in enumerate(zip(scores, labels)):
+                bs = batch_size if batch_size is not None else (scores[0].shape[0])
+                for i, sample in enumerate(s.tolist()):
+                    fh.write(f"{i + batch_idx * bs}:\t{sample}\n{y[i]}\n")
+                    n += 1
+            fh.flush()
+        finally:
+            if own:
+                fh.close()
+        return n
 
 
 class GraphedStoreStep:

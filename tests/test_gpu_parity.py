@@ -220,3 +220,37 @@ def test_vector_edge_backward_two_column_variant(name):
     for key, p in model.named_parameters():
         if grads[key] is not None:
             assert rel_err(p.grad.cpu(), grads[key]) < TOL, key
+
+
+def test_vector_edges_fused_trainer_and_bf16_mode():
+    """Vector edges through the fused Trainer path (bit-identical to autograd) and in bf16 feature mode
+    (same stated tolerances as the scalar-edge bf16 test: 2e-3 scores, 3e-2 gradients)."""
+    path = [p for p in CASES if os.path.basename(p) == "wd_b8_vector.pt"][0]
+    cfg, batch, sd, fx = load_case(path)
+    dbatch = [t.cuda() for t in batch]
+    m1, m2 = _cuda_model(cfg, sd), _cuda_model(cfg, sd)
+    drin_b200.TripletLoss(cfg.triplet_margin)(dbatch[-1], m1(dbatch[:-1])).backward()
+    tr = drin_b200.Trainer(m2, margin=cfg.triplet_margin)
+    loss = tr.forward_backward(dbatch)
+    assert abs(float(loss) - fx["loss"]) <= TOL * abs(fx["loss"])
+    fused = m2._grad_views()
+    for k, p in m1.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, fused[k]), k
+    tr.step(dbatch)                                          # Adam over the 30-tensor flat buffer, dead w_m/w_u/w_v masked
+    dead = [k for k in sd if k.startswith("gcn_layers.1.w_") and not k.startswith("gcn_layers.1.w_h")]
+    assert len(dead) == 6
+    for k, p in m2.named_parameters():
+        changed = not torch.equal(p.detach().cpu(), sd[k])
+        assert changed == (k not in dead), k
+    feats = (0, 4, 5, 7, 9, 10)
+    rb = [t.to(torch.bfloat16).float() if i in feats else t for i, t in enumerate(batch)]
+    s_ref, l_ref, g_ref = O.train_step_grads(sd, rb[:-1], rb[-1], cfg)
+    model = _cuda_model(cfg, sd)
+    db = [t.cuda().to(torch.bfloat16) if i in feats else t.cuda() for i, t in enumerate(batch)]
+    scores = model(db[:-1])
+    drin_b200.TripletLoss(cfg.triplet_margin)(db[-1], scores).backward()
+    assert rel_err(scores.detach().cpu(), s_ref) < 2e-3
+    for k, p in model.named_parameters():
+        if g_ref[k] is not None:
+            assert rel_err(p.grad.cpu(), g_ref[k]) < 3e-2, k

@@ -86,3 +86,50 @@ def test_backward_with_layers_done_event_gives_identical_gradients():
     torch.cuda.synchronize()
     assert ev.query()
     assert torch.equal(plain, with_event)
+
+
+def test_evaluator_matches_the_reference_test_loop(tmp_path):
+    """Evaluator = MELModel._forward_step(type=2) over a test split (upstream train.py:30-43): per-step TripletLoss,
+    threshold top-k accuracy with ties as hits (common/utils.py:60-66), and the test-result.txt text format, with a
+    single device->host read at the end."""
+    import io
+
+    from drin_b200.synthetic import make_batch, spread_weights
+    from oracle import drin_oracle as O
+    cfg = O.DrinConfig(num_candidates_model=11)
+    sd = spread_weights(O.init_state(cfg, 0))
+    model = drin_b200.Model(num_candidates_model=11)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    ev = drin_b200.Evaluator(model, margin=cfg.triplet_margin, top_k=(1, 3, 5), keep_scores=True)
+    batches = [make_batch("wikidiverse", 6, 70 + i, 10) for i in range(3)]
+    ref_scores, ref_losses, hits = [], [], {1: 0, 3: 0, 5: 0}
+    for b in batches:
+        ev.step([t.cuda() for t in b])
+        s = O.forward(sd, b[:-1], cfg)
+        ref_scores.append(s)
+        ref_losses.append(float(O.triplet_loss(b[-1], s, cfg.triplet_margin)))
+        for k in hits:
+            hits[k] += O.topk_hits(s, b[-1], k)
+    out = ev.compute()
+    assert out["mentions"] == 18
+    assert abs(out["loss"] - sum(ref_losses) / 3) <= 1e-4 * abs(sum(ref_losses) / 3)
+    assert {k: round(v * 18) for k, v in out["topk"].items()} == hits
+    buf = io.StringIO()
+    assert ev.write_results(buf, batch_size=6) == 18
+    # the reference's own formatting expression (train.py:41-42) applied to the oracle's scores
+    lines = buf.getvalue().split("\n")
+    want = "".join(f"{i + bi * 6}:\t{sample}\n{b[-1][i]}\n" for bi, (s, b) in enumerate(zip(ref_scores, batches))
+                   for i, sample in enumerate(s.tolist())).split("\n")
+    assert len(lines) == len(want)
+    for got, ref in zip(lines, want):
+        if ":\t" in got:
+            gi, gs = got.split(":\t")
+            ri, rs = ref.split(":\t")
+            assert gi == ri
+            assert torch.allclose(torch.tensor(eval(gs)), torch.tensor(eval(rs)), atol=1e-5)
+        else:
+            assert got == ref          # the label line: repr of the uint8 one-hot row
+    path = tmp_path / "test-result.txt"
+    ev.write_results(str(path), batch_size=6)
+    assert path.read_text() == buf.getvalue()
