@@ -309,7 +309,7 @@ def run_ours(args):
             def drain():
                 torch.cuda.current_stream().wait_event(feeder.slots[state["slot"]]["ready"])
 
-            ms = timed(e2e_step, max(args.steps // 2, 3), 2, after=drain)
+            ms = timed(e2e_step, max(args.steps // 2, 3), 3, after=drain)
             nbytes = feeder.last_bytes
             del feeder
             return ms, nbytes
