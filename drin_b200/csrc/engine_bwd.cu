@@ -87,7 +87,7 @@ static int backward_vector_layers(const drin_config& c, const drin_params& p, Wo
   for (int l = L - 1; l >= 0; --l) {
     const LayerWs& lw = ws.layer[l];
     const drin_layer_params& lg = grads.layer[l];
-    float* vec_part = ws.vec_part + (size_t)l * vec_layer_ctas() * 2 * D;
+    float* vec_part = ws.vec_part + (size_t)l * vec_layer_ctas() * 3 * D;
     float* rows_part = ws.rows_part + (size_t)l * vec_rows_ctas() * 4 * D;
     if (l == L - 1) {
       const drin_layer_params& lp = p.layer[l];

@@ -23,7 +23,7 @@
 
 namespace drin {
 
-static constexpr int VEC_GRID = 148 * 4;      // persistent CTAs (rows of the partial-sum buffers)
+static constexpr int VEC_GRID = 148 * 8;      // upper bound of the persistent grid (rows of the partial-sum buffers)
 static constexpr int VR_NW = 4;               // warps per CTA of vec_rows_bwd
 static constexpr int VR_CTAS = 148 * 3;
 
@@ -325,33 +325,48 @@ __global__ void __launch_bounds__(D / W, W == 4 ? 3 : 2) vec_layer_bwd_kernel(co
 
 static int g_vec_bwd_width = 0;          // 0 auto, 2 or 4 columns per thread (test / A-B hook)
 void debug_set_vec_bwd_width(int v) { g_vec_bwd_width = (v == 2 || v == 4) ? v : 0; }
+static int g_vec_ctas_per_sm = 0;        // 0 auto (as many as are resident), else an upper bound (A-B hook)
+void debug_set_vec_ctas_per_sm(int v) { g_vec_ctas_per_sm = v > 0 ? v : 0; }
+
+// Persistent grid = (resident CTAs per SM) x 148, so that every CTA of the grid-stride loop over the mentions is on an
+// SM from the start: a grid larger than what is resident would run its tail at a fraction of the occupancy.
+template <typename K>
+static int launch_vec_kernel(K kernel, int threads, cudaStream_t stream, const VecLayerArgs& a, int* grid_out) {
+  int resident = 0;
+  DRIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, threads, 0));
+  if (resident < 1) resident = 1;
+  if (resident > VEC_GRID / 148) resident = VEC_GRID / 148;
+  if (g_vec_ctas_per_sm && resident > g_vec_ctas_per_sm) resident = g_vec_ctas_per_sm;
+  const int grid = a.B < 148 * resident ? a.B : 148 * resident;
+  kernel<<<grid, threads, 0, stream>>>(a);
+  if (grid_out) *grid_out = grid;
+  return DRIN_OK;
+}
 
 template <int D, int W, bool BWD, bool FULL, bool DYN>
-static void launch_vec(cudaStream_t stream, const VecLayerArgs& a, int grid, int edge) {
+static int launch_vec(cudaStream_t stream, const VecLayerArgs& a, int edge, int* grid) {
   if (edge == EDGE_SCALAR) {
-    if (BWD) vec_layer_bwd_kernel<D, W, FULL, DYN, EDGE_SCALAR><<<grid, D / W, 0, stream>>>(a);
-    else vec_layer_fwd_kernel<D, W, FULL, DYN, EDGE_SCALAR><<<grid, D / W, 0, stream>>>(a);
+    if (BWD) return launch_vec_kernel(vec_layer_bwd_kernel<D, W, FULL, DYN, EDGE_SCALAR>, D / W, stream, a, grid);
+    return launch_vec_kernel(vec_layer_fwd_kernel<D, W, FULL, DYN, EDGE_SCALAR>, D / W, stream, a, grid);
   } else if (edge == EDGE_VECTOR) {
-    if (BWD) vec_layer_bwd_kernel<D, W, FULL, DYN, EDGE_VECTOR><<<grid, D / W, 0, stream>>>(a);
-    else vec_layer_fwd_kernel<D, W, FULL, DYN, EDGE_VECTOR><<<grid, D / W, 0, stream>>>(a);
-  } else {
-    if (BWD) vec_layer_bwd_kernel<D, W, FULL, DYN, EDGE_AFFINE><<<grid, D / W, 0, stream>>>(a);
-    else vec_layer_fwd_kernel<D, W, FULL, DYN, EDGE_AFFINE><<<grid, D / W, 0, stream>>>(a);
+    if (BWD) return launch_vec_kernel(vec_layer_bwd_kernel<D, W, FULL, DYN, EDGE_VECTOR>, D / W, stream, a, grid);
+    return launch_vec_kernel(vec_layer_fwd_kernel<D, W, FULL, DYN, EDGE_VECTOR>, D / W, stream, a, grid);
   }
+  if (BWD) return launch_vec_kernel(vec_layer_bwd_kernel<D, W, FULL, DYN, EDGE_AFFINE>, D / W, stream, a, grid);
+  return launch_vec_kernel(vec_layer_fwd_kernel<D, W, FULL, DYN, EDGE_AFFINE>, D / W, stream, a, grid);
 }
 
 template <int W, bool BWD>
-static void launch_vec_shape(cudaStream_t stream, const VecLayerArgs& a, int grid, int edge) {
+static int launch_vec_shape(cudaStream_t stream, const VecLayerArgs& a, int edge, int* grid) {
   if (a.full) {
-    if (a.dyn) launch_vec<768, W, BWD, true, true>(stream, a, grid, edge);
-    else launch_vec<768, W, BWD, true, false>(stream, a, grid, edge);
-  } else {
-    launch_vec<768, W, BWD, false, false>(stream, a, grid, edge);
+    if (a.dyn) return launch_vec<768, W, BWD, true, true>(stream, a, edge, grid);
+    return launch_vec<768, W, BWD, true, false>(stream, a, edge, grid);
   }
+  return launch_vec<768, W, BWD, false, false>(stream, a, edge, grid);
 }
 
 template <bool BWD>
-static int vec_layer_dispatch(cudaStream_t stream, const VecLayerArgs& a) {
+static int vec_layer_dispatch(cudaStream_t stream, const VecLayerArgs& a, int* grid) {
   if (a.D != 768) return fail(DRIN_ERR_ARG, "vector-edge GCN layer: gcn_embed_dim %d not built (768 only)", a.D);
   const int edge = a.edge_a ? EDGE_AFFINE : (a.e_scalar ? EDGE_SCALAR : EDGE_VECTOR);
   if (!a.xa || (edge == EDGE_VECTOR && !a.q_in) || (edge == EDGE_AFFINE && (!a.edge_bv || !a.edge_w1 || !a.e_scalar)))
@@ -366,26 +381,24 @@ static int vec_layer_dispatch(cudaStream_t stream, const VecLayerArgs& a) {
         (edge == EDGE_VECTOR && !a.dq_hi) || (edge == EDGE_AFFINE && (!a.da_hi || !a.dbv_hi)))
       return fail(DRIN_ERR_ARG, "vector-edge GCN layer backward: missing buffers");
   }
-  const int grid = a.B < VEC_GRID ? a.B : VEC_GRID;
   // 2 columns per thread (D/2 threads per mention) is kept as an A/B option for the backward kernels: it needs 70-80
   // registers against 84-96 at 4 columns, i.e. no more resident warps and half the bytes in flight per thread
   const int width = (BWD && g_vec_bwd_width == 2) ? 2 : 4;
-  if (width == 2) launch_vec_shape<2, BWD>(stream, a, grid, edge);
-  else launch_vec_shape<4, BWD>(stream, a, grid, edge);
+  if (width == 2) DRIN_TRY((launch_vec_shape<2, BWD>(stream, a, edge, grid)));
+  else DRIN_TRY((launch_vec_shape<4, BWD>(stream, a, edge, grid)));
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }
 
 int vec_layer_fwd(cudaStream_t stream, const VecLayerArgs& a) {
   prof::Scope prof_scope(stream, prof::GCN_FWD);
-  return vec_layer_dispatch<false>(stream, a);
+  return vec_layer_dispatch<false>(stream, a, nullptr);
 }
 
-// partials: [min(B, vec_layer_ctas())][3][D]
+// partials: [*partial_rows][3][D] with *partial_rows = the launched grid <= vec_layer_ctas()
 int vec_layer_bwd(cudaStream_t stream, const VecLayerArgs& a, int* partial_rows) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
-  if (partial_rows) *partial_rows = a.B < VEC_GRID ? a.B : VEC_GRID;
-  return vec_layer_dispatch<true>(stream, a);
+  return vec_layer_dispatch<true>(stream, a, partial_rows);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -254,3 +254,26 @@ def test_vector_edges_fused_trainer_and_bf16_mode():
     for k, p in model.named_parameters():
         if g_ref[k] is not None:
             assert rel_err(p.grad.cpu(), g_ref[k]) < 3e-2, k
+
+
+@pytest.mark.parametrize("B,layers", [(1300, 2), (700, 3)])
+def test_vector_edges_at_scale_match_oracle(B, layers):
+    """Vector edges at batch sizes where the persistent grids wrap (several mentions per CTA, every per-CTA partial
+    row in use, cta_group::2 GEMM tiles): scores, loss and every gradient against the oracle on the host."""
+    from drin_b200.synthetic import make_batch, spread_weights
+    cfg = O.DrinConfig(num_candidates_model=11, num_gcn_layers=layers, gcn_edge_feature="vector")
+    batch = make_batch("wikidiverse", B, 23, 10)
+    sd = spread_weights(O.init_state(cfg, 0))
+    s_ref, l_ref, g_ref = O.train_step_grads(sd, batch[:-1], batch[-1], cfg)
+    model = _cuda_model(cfg, sd)
+    db = [t.cuda() for t in batch]
+    scores = model(db[:-1])
+    loss = drin_b200.TripletLoss(cfg.triplet_margin)(db[-1], scores)
+    loss.backward()
+    assert rel_err(scores.detach().cpu(), s_ref) < TOL
+    assert abs(float(loss) - float(l_ref)) <= TOL * abs(float(l_ref))
+    for k, p in model.named_parameters():
+        if g_ref[k] is not None:
+            assert rel_err(p.grad.cpu(), g_ref[k]) < TOL, k
+        else:
+            assert p.grad is None, k
