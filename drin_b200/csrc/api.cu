@@ -134,6 +134,7 @@ int drin_debug_option(const char* name, int32_t value) {
   else if (!strcmp(name, "layer_fwd_variant")) debug_set_layer_fwd_variant(value);
   else if (!strcmp(name, "layer_bwd_variant")) debug_set_layer_bwd_variant(value);
   else if (!strcmp(name, "defer_reductions")) debug_set_defer_reductions(value);
+  else if (!strcmp(name, "row_slice_min")) debug_set_row_slice_min(value);
   else if (!strcmp(name, "vec_bwd_width")) debug_set_vec_bwd_width(value);
   else if (!strcmp(name, "vec_ctas_per_sm")) debug_set_vec_ctas_per_sm(value);
   else return fail(DRIN_ERR_ARG, "drin_debug_option: unknown option '%s'", name);

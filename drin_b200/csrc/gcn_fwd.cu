@@ -433,8 +433,11 @@ static int launch_layer_fwd_warp(cudaStream_t stream, const LayerFwdArgs& a) {
   return DRIN_OK;
 }
 
+static int g_row_slice_min = 8;          // fewest candidates a slice may hold (test / A-B hook)
+void debug_set_row_slice_min(int v) { g_row_slice_min = v > 0 ? v : 8; }
+
 int row_kernel_slices(int B, int C) {
-  const int max_slices = C / 8;                       // at least 8 candidates per slice
+  const int max_slices = C / g_row_slice_min;         // at least 8 candidates per slice
   if (max_slices < 2) return 1;
   const long long warps = 148LL * 8;
   int best = 1;

@@ -109,6 +109,7 @@ void debug_set_score_fwd_variant(int v);
 void debug_set_layer_fwd_variant(int v);
 void debug_set_layer_bwd_variant(int v);
 void debug_set_defer_reductions(int v);
+void debug_set_row_slice_min(int v);
 
 struct LayerBwdArgs {
   int B, C, D;

@@ -1,6 +1,6 @@
-"""A/B of the vector-edge kernels' launch options on one B200 (test hooks of drin_debug_option):
-    python scripts/vector_ab.py [--batch 4096]
-prints ms/step and the GCN forward / backward stage times for vec_ctas_per_sm in {auto, 2..8} and vec_bwd_width 2."""
+"""A/B of kernel launch options on one B200 (the test hooks of drin_debug_option):
+    python scripts/ab.py [--edge-feature vector] [--batch 4096] --option vec_ctas_per_sm --values 0,2,3,4,5,6,8
+prints ms/step and the per-stage device times of the train step for every value of the option."""
 import argparse
 import ctypes as C
 import os
@@ -21,11 +21,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--edge-feature", default="scaler")
+    ap.add_argument("--option", default="vec_ctas_per_sm")
+    ap.add_argument("--values", default="0,2,3,4,5,6,8")
+    ap.add_argument("--reset", type=int, default=0, help="value that restores the default")
     args = ap.parse_args()
     lib = _lib.load()
     batch = make_batch("wikidiverse", args.batch, seed=1, num_candidates=10, device="cuda", generate_on_device=True)
     torch.manual_seed(0)
-    model = drin_b200.Model(num_candidates_model=11, gcn_edge_feature="vector", num_gcn_layers=args.layers).cuda()
+    model = drin_b200.Model(num_candidates_model=11, gcn_edge_feature=args.edge_feature, num_gcn_layers=args.layers).cuda()
     tr = drin_b200.Trainer(model)
 
     def opt(name, v):
@@ -50,17 +54,13 @@ def main():
         cnt = (C.c_longlong * n)()
         lib.drin_profile_collect(ms, fl, by, cnt)
         lib.drin_profile_enable(0)
-        print(f"{label:>22s}: {e0.elapsed_time(e1) / 10:.3f} ms/step  gcn_fwd {ms[2] / 5:.3f}  gcn_bwd {ms[3] / 5:.3f}  "
-              f"gemm {ms[0] / 5:.3f}", flush=True)
+        print(f"{label:>26s}: {e0.elapsed_time(e1) / 10:.3f} ms/step  gcn_fwd {ms[2] / 5:.3f}  gcn_bwd {ms[3] / 5:.3f}  "
+              f"score {ms[4] / 5:.3f}  gemm {ms[0] / 5:.3f}", flush=True)
 
-    run("auto")
-    for k in (2, 3, 4, 5, 6, 8):
-        opt("vec_ctas_per_sm", k)
-        run(f"ctas_per_sm<={k}")
-    opt("vec_ctas_per_sm", 0)
-    opt("vec_bwd_width", 2)
-    run("bwd 2 cols/thread")
-    opt("vec_bwd_width", 0)
+    for v in [int(x) for x in args.values.split(",")]:
+        opt(args.option, v)
+        run(f"{args.option}={v}")
+    opt(args.option, args.reset)
 
 
 if __name__ == "__main__":
