@@ -20,13 +20,14 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     dataset, cands = ("wikidiverse", 10)
+    edge_feature = sys.argv[1] if len(sys.argv) > 1 else "scaler"
     B = 16 * world
     batch = make_batch(dataset, B, 21, cands)
-    cfg = O.DrinConfig(num_candidates_model=cands + 1, triplet_margin=0.05)
+    cfg = O.DrinConfig(num_candidates_model=cands + 1, triplet_margin=0.05, gcn_edge_feature=edge_feature)
     sd = spread_weights(O.init_state(cfg, 0))
 
     def model():
-        m = drin_b200.Model(num_candidates_model=cands + 1)
+        m = drin_b200.Model(num_candidates_model=cands + 1, gcn_edge_feature=edge_feature)
         m.load_state_dict(sd)
         return m.to(dev)
 

@@ -14,9 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_two_gpu_step_equals_single_gpu_full_batch_step():
+@pytest.mark.parametrize("edge_feature", ["scaler", "vector"])
+def test_two_gpu_step_equals_single_gpu_full_batch_step(edge_feature):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "gpu_dp_check.py")]
+           "127.0.0.1", "--master-port", "29533" if edge_feature == "scaler" else "29534",
+           os.path.join(ROOT, "scripts", "gpu_dp_check.py"), edge_feature]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     line = [l for l in out.stdout.splitlines() if l.startswith("DPCHECK ")]
     assert line, out.stdout[-2000:] + out.stderr[-2000:]

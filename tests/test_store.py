@@ -160,16 +160,17 @@ def test_indexed_training_matches_oracle():
 
 
 @pytest.mark.gpu
-def test_graphed_step_replays_bit_identically_to_eager_steps():
+@pytest.mark.parametrize("edge_feature", ["scaler", "vector"])
+def test_graphed_step_replays_bit_identically_to_eager_steps(edge_feature):
     """The captured CUDA graph of the whole step (front end .. Adam, device-side step count) gives the same bits as
-    eager steps over the same index batches."""
+    eager steps over the same index batches (scalar and vector edges)."""
     tables, C = make_tables("wikidiverse")
     store = FeatureStore("wikidiverse", tables, C, device="cuda")
     batches = [[0, 3, 5, 8], [1, 2, 6, 7], [4, 4, 0, 2]]
     outs = []
     for graphed in (False, True):
         torch.manual_seed(0)
-        model = drin_b200.Model(num_candidates_model=C).cuda()
+        model = drin_b200.Model(num_candidates_model=C, gcn_edge_feature=edge_feature).cuda()
         tr = drin_b200.Trainer(model, lr=1e-3)
         losses = []
         if graphed:
