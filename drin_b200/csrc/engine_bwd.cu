@@ -293,6 +293,8 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     if (!partA || !partB || !partC) return fail(DRIN_ERR_WORKSPACE, "internal: column-sum arena exhausted");
     la.partials = partA;
     la.slices = ws.slices; la.slice_part = ws.slice_part; la.slice_dbeta = ws.slice_dbeta;
+    int rowsA = layer_bwd_ctas();
+    la.partial_rows = &rowsA;
     DRIN_TRY(gcn_layer_bwd(stream, la));
 
     if (lw.dyn) {
@@ -324,9 +326,9 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     DRIN_TRY(mention_bwd_finish(stream, ma));
     if (l > 0) {
       const drin_layer_params& pg = grads.layer[l - 1];
-      DRIN_TRY(df.add_colsum(partA, layer_bwd_ctas(), partB, backward_ctas(), 3, pg.ln_w, pg.ln_b, pg.b_h));
+      DRIN_TRY(df.add_colsum(partA, rowsA, partB, backward_ctas(), 3, pg.ln_w, pg.ln_b, pg.b_h));
     } else {
-      DRIN_TRY(df.add_colsum(partA, layer_bwd_ctas(), nullptr, 0, 3, grads.b_et, grads.b_ei, nullptr));
+      DRIN_TRY(df.add_colsum(partA, rowsA, nullptr, 0, 3, grads.b_et, grads.b_ei, nullptr));
       DRIN_TRY(df.add_colsum(partB, backward_ctas(), nullptr, 0, 3, grads.b_mt, grads.b_mi, nullptr));
     }
   }

@@ -1169,13 +1169,134 @@ static int launch_layer_bwd_warp(cudaStream_t stream, const LayerBwdArgs& a) {
   return DRIN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// gcn_layer_bwd, column-wise version for the FIRST layer.  Its candidate rows are projection outputs (no LayerNorm in
+// front) and its edges are inputs (no edge gradient), so nothing in its backward is a dot product along D: a thread
+// owns four columns of one mention and walks the candidates -- no shuffles, no shared memory, 16-byte coalesced
+// accesses, sums over candidates in registers (candidate order -> deterministic).  Same outputs as the warp kernel.
+// ---------------------------------------------------------------------------------------------
+static constexpr int COL_CTAS_MAX = 148 * 3;     // rows of the partial buffer this kernel may use (= BW_CTAS rows per region)
+
+__device__ __forceinline__ float4 col_ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 col_fma(float s, const float4& a, const float4& c) {
+  return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+}
+__device__ __forceinline__ void col_acc(float4& c, const float4& a) { c.x += a.x; c.y += a.y; c.z += a.z; c.w += a.w; }
+__device__ __forceinline__ void col_st_planes(bf16* hi, bf16* lo, long long idx, const float4& v) {
+  uint32_t h0, l0, h1, l1;
+  split_bf16x2(v.x, v.y, h0, l0);
+  split_bf16x2(v.z, v.w, h1, l1);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h0, h1);
+  if (lo) *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l0, l1);
+}
+
+template <int D, bool FULL, bool DYN>
+__global__ void __launch_bounds__(D / 4, 3) gcn_layer0_bwd_col_kernel(const LayerBwdArgs a) {
+  const int col = threadIdx.x * 4;
+  const long long B = a.B, C = a.C, BC = B * C;
+  const float invC = 1.0f / (float)a.C, invD = 1.0f / (float)D;
+  const float* dz_et = a.dz + (FULL ? 2 * B : B) * D;
+  const float* dz_ei = FULL ? a.dz + (2 * B + BC) * D : nullptr;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 p_et = zero, p_ei = zero;               // db_et, db_ei (bias gradients of the entity projections)
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const float4 dzmt = col_ld(a.dz + b * D + col);
+    const float4 dzmi = FULL ? col_ld(a.dz + (B + b) * D + col) : zero;
+    float4 gmt = zero, gmi = zero;
+    if (DYN) {
+      gmt = col_ld(a.g + b * D + col);
+      gmi = col_ld(a.g + (B + b) * D + col);
+    }
+    float4 A_mt = dzmt, A_mi = dzmi, G_mt = zero, G_mi = zero;     // dxm = dz_m + messages from the candidate rows
+    float dbeta_mt = 0.f, dbeta_mi = 0.f;
+    for (long long c = 0; c < C; ++c) {
+      const long long r = b * C + c;
+      const float4 dzet = col_ld(dz_et + r * D + col);
+      const float4 dzei = FULL ? col_ld(dz_ei + r * D + col) : zero;
+      float e[4], dd[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k] = a.edges_in[k * BC + r] * a.en[k];                  // enable mask (model.py:122)
+        if (DYN) {
+          const float o = a.edges_out[k * BC + r];
+          dd[k] = a.dedges_out[k * BC + r] * o * (1.f - o) * invD;    // sigmoid backward of the edge update, / D of the mean
+        }
+      }
+      // z_et = et + e0 mt + e2 mi, z_ei = ei + e1 mt + e3 mi, z_m += mean_c(e . cand);  edge update: v . g_u
+      float4 det = col_fma(e[0] * invC, dzmt, dzet);
+      float4 dei = col_fma(e[1] * invC, dzmt, dzei);
+      if (FULL) {
+        det = col_fma(e[2] * invC, dzmi, det);
+        dei = col_fma(e[3] * invC, dzmi, dei);
+      }
+      A_mt = col_fma(e[0], dzet, A_mt);
+      A_mi = col_fma(e[2], dzet, A_mi);
+      if (FULL) {
+        A_mt = col_fma(e[1], dzei, A_mt);
+        A_mi = col_fma(e[3], dzei, A_mi);
+      }
+      if (DYN) {
+        const float4 xet = col_ld(a.x_et + r * D + col);
+        const float4 xei = col_ld(a.x_ei + r * D + col);
+        det = col_fma(dd[0], gmt, col_fma(dd[2], gmi, det));
+        dei = col_fma(dd[1], gmt, col_fma(dd[3], gmi, dei));
+        G_mt = col_fma(dd[0], xet, col_fma(dd[1], xei, G_mt));
+        G_mi = col_fma(dd[2], xet, col_fma(dd[3], xei, G_mi));
+        dbeta_mt += dd[0] + dd[1];
+        dbeta_mi += dd[2] + dd[3];
+      }
+      col_acc(p_et, det);
+      col_acc(p_ei, dei);
+      col_st_planes(a.dcand_hi, a.dcand_lo, (2 * B + r) * D + col, det);
+      col_st_planes(a.dcand_hi, a.dcand_lo, (2 * B + BC + r) * D + col, dei);
+    }
+    *reinterpret_cast<float4*>(a.dxm + b * D + col) = A_mt;
+    *reinterpret_cast<float4*>(a.dxm + (B + b) * D + col) = A_mi;
+    if (DYN) {
+      col_st_planes(a.dg_hi, a.dg_lo, b * D + col, G_mt);
+      col_st_planes(a.dg_hi, a.dg_lo, (B + b) * D + col, G_mi);
+      if (threadIdx.x == 0) {
+        a.dbeta[b] = dbeta_mt;
+        a.dbeta[B + b] = dbeta_mi;
+      }
+    }
+  }
+  float* part = a.partials + (long long)blockIdx.x * 3 * D + col;
+  *reinterpret_cast<float4*>(part) = p_et;
+  *reinterpret_cast<float4*>(part + D) = p_ei;
+  *reinterpret_cast<float4*>(part + 2 * D) = zero;
+}
+
+template <int D, bool FULL, bool DYN>
+static int launch_layer0_bwd_col(cudaStream_t stream, const LayerBwdArgs& a) {
+  int resident = 0;
+  DRIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, gcn_layer0_bwd_col_kernel<D, FULL, DYN>, D / 4, 0));
+  if (resident < 1) resident = 1;
+  int grid = 148 * resident;                     // every CTA of the grid-stride loop resident from the start
+  if (grid > COL_CTAS_MAX) grid = COL_CTAS_MAX;
+  if (grid > a.B) grid = a.B;
+  gcn_layer0_bwd_col_kernel<D, FULL, DYN><<<grid, D / 4, 0, stream>>>(a);
+  DRIN_LAUNCH_CHECK();
+  if (a.partial_rows) *a.partial_rows = grid;
+  return DRIN_OK;
+}
+
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a_in) {
   prof::Scope prof_scope(stream, prof::GCN_BWD);
   if (a_in.D != 768) return fail(DRIN_ERR_ARG, "gcn_layer_bwd: gcn_embed_dim %d not built (768 only)", a_in.D);
   constexpr int D = 768;
   LayerBwdArgs a = a_in;
   if (a.slices < 1 || !a.slice_part || !a.slice_dbeta) a.slices = 1;
+  if (a.partial_rows) *a.partial_rows = BS_GRID;
   const bool warp_kernel = g_layer_bwd_variant < 0 ? (long long)a.B * a.slices >= BS_GRID * 7 : g_layer_bwd_variant >= 1;
+  // first layer (no LayerNorm in front, edges are inputs): nothing is a dot product along D -> column-wise kernel.
+  // Variant 2 forces it (tests), variant 0 / 1 force the other two families.
+  const bool first_layer = !a.ln_gamma && !a.dedges_in && a.partial_rows;
+  if (first_layer && (g_layer_bwd_variant == 2 || (g_layer_bwd_variant < 0 && warp_kernel && a.slices == 1))) {
+    const bool dyn = a.full && a.g != nullptr;
+    if (a.full) return dyn ? launch_layer0_bwd_col<D, true, true>(stream, a) : launch_layer0_bwd_col<D, true, false>(stream, a);
+    return launch_layer0_bwd_col<D, false, false>(stream, a);
+  }
   if (warp_kernel) {
     // 7 warps x 30 KB (full layers) or 8 warps x 15 KB (last layer) of private shared memory per SM
     const bool ln = a.ln_gamma != nullptr;

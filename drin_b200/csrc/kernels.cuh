@@ -131,6 +131,8 @@ struct LayerBwdArgs {
   int slices;                 // candidate slices (row_kernel_slices); > 1: mention-side results by a finish kernel
   float* slice_part;          // [B * slices][4][D]: A_mt, A_mi, G_mt, G_mi partial sums of the slice
   float* slice_dbeta;         // [B * slices][2]
+  int* partial_rows;          // HOST out (may be null): rows of `partials` the launch wrote (layer_bwd_ctas() unless the
+                              // column-wise first-layer kernel ran, which may use up to backward_ctas() rows)
 };
 int gcn_layer_bwd(cudaStream_t stream, const LayerBwdArgs& a);
 

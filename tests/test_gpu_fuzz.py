@@ -33,8 +33,10 @@ def _cases():
             seed=100 + i,
             kw=dict(entity_tokens=rng.choice([4, 5, 16]), mention_tokens=rng.choice([24, 32])) if wm else {},
         ))
-    for c in out:
+    for i, c in enumerate(out):
         c["vector"] = False
+        if i % 4 == 1:
+            c["variant"] = 2          # warp kernels + the column-wise first-layer backward (drawn values stay untouched)
     rng = random.Random(20251019)            # gcn_edge_feature="vector" cases (appended: the cases above keep their draws)
     for i in range(10):
         wm = i % 3 == 2

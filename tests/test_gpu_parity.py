@@ -26,8 +26,9 @@ def _option(name, value):
 
 @pytest.fixture
 def kernel_variants(request):
-    """Force the kernel variants that are normally picked only at full-size batches (warp-autonomous row kernels),
-    so the golden cases exercise them too; reset to automatic afterwards."""
+    """Force the kernel variants that are normally picked only at full-size batches (1: warp-autonomous row kernels;
+    2: the same plus the column-wise first-layer backward kernel), so the golden cases exercise them too; reset to
+    automatic afterwards."""
     forced = request.param
     for name in VARIANT_OPTIONS:
         _option(name, forced)
@@ -47,7 +48,7 @@ def _cuda_model(cfg, sd):
     return m.cuda()
 
 
-@pytest.mark.parametrize("kernel_variants", [-1, 1], ids=["auto", "warp-kernels"], indirect=True)
+@pytest.mark.parametrize("kernel_variants", [-1, 1, 2], ids=["auto", "warp-kernels", "warp+column-kernels"], indirect=True)
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-3] for p in CASES])
 def test_train_step_matches_reference_golden_and_oracle(path, kernel_variants):
     cfg, batch, sd, fx = load_case(path)
