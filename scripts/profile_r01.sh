@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 echo "launch list rc=$?"
 # kernel regex : launches to skip : launches to capture : output name  (the GEMM capture covers the four input projections
 # of the first ranking forward, the largest being the entity-image projection)
-for spec in "gemm_tcgen05:120:4:prof_gemm" "gcn_layer_bwd_warp:2:2:prof_layer_bwd" "frontend_kernel:1:1:prof_frontend" "gcn_layer_fwd_warp:2:2:prof_layer_fwd" "score_bwd_warp:1:1:prof_score_bwd" "score_warp:1:1:prof_score_fwd"; do
+for spec in "gemm_tcgen05:120:4:prof_gemm" "gcn_layer_bwd_warp:1:1:prof_layer_bwd" "gcn_layer0_bwd_col:1:1:prof_layer0_bwd_col" "frontend_kernel:1:1:prof_frontend" "gcn_layer_fwd_warp:2:2:prof_layer_fwd" "score_bwd_warp:1:1:prof_score_bwd" "score_warp:1:1:prof_score_fwd"; do
   IFS=: read -r pat skip cnt out <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c $cnt -f -o gpurun_out/$out $CMD > gpurun_out/ncu_$out.log 2>&1
   echo "$out rc=$?"
