@@ -200,7 +200,11 @@ int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name,
                       int64_t* rows, int64_t* cols);
 
 /* Test hook: force a kernel variant that is normally chosen from the problem size (value -1 = automatic).
- * Options: "score_bwd_variant" (0 CTA-per-mention kernel, 1 warp-per-mention kernel).  Not part of the drop-in surface. */
+ * Options: "score_fwd_variant", "score_bwd_variant", "layer_fwd_variant", "layer_bwd_variant" (0 CTA-per-mention / staged kernel,
+ * 1 warp-per-mention kernel; "layer_bwd_variant" 2 = 1 plus the column-wise first-layer backward kernel), "defer_reductions"
+ * (0: every split-K / column-sum reduction right after its producer), "row_slice_min" (fewest candidates per slice of the sliced
+ * row kernels, default 8), "vec_bwd_width" (2 | 4 columns per thread of the vector-edge backward kernels), "vec_ctas_per_sm"
+ * (upper bound on the resident-CTA grid of the vector-edge kernels, 0 = all).  Not part of the drop-in surface. */
 int drin_debug_option(const char* name, int32_t value);
 
 #ifdef __cplusplus
