@@ -40,6 +40,26 @@ def test_workspace_plan_and_config_errors_need_no_gpu():
         eng.workspace_bytes(bad)
 
 
+def test_vector_edge_workspace_plan():
+    """Workspace plan of the vector-edge path (csrc/engine.cu: plan_vector): the two-layer model needs no [4BC, D] edge
+    matrices thanks to the first-layer shortcut, every further layer adds them; static edges and one layer fall back to
+    the scalar plan exactly."""
+    pb = E.Problem(4096, 11, 128, 0, 49, 3, 1, 768, 2048, E.FP32)
+    edge = 4 * 4096 * 11 * 768                      # elements of one [4BC, D] matrix
+
+    def need(layers, training, **kw):
+        eng = E.Engine(layers, **kw)
+        return eng.workspace_bytes(eng.config(pb, training))
+
+    s2, v2, v3, v4 = need(2, True), need(2, True, vector_edges=True), need(3, True, vector_edges=True), need(4, True, vector_edges=True)
+    assert s2 < v2 < s2 + 4 * edge * 4              # two layers: row-sized extras only (no m / q / dm / dq: 6 edge matrices)
+    assert v3 - v2 > 3 * edge * 4                   # m planes + q per general layer, dm + dq planes once
+    assert v4 - v3 > 2 * edge * 4
+    assert need(2, True, vector_edges=True, static_edges=True) == need(2, True, static_edges=True)
+    assert need(1, True, vector_edges=True) == need(1, True)
+    assert need(2, False, vector_edges=True) < v2 < 16 << 30
+
+
 def test_model_is_a_drop_in_for_the_reference_constructor():
     torch.manual_seed(0)
     m = drin_b200.Model()
