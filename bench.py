@@ -115,31 +115,59 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port, loop-faithful like the reference's Python loops)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="scaler"):
+def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="scaler", kind="auto"):
+    """Time the train step and the ranking forward of the reference's CPU path on all host cores.
+
+    kind "reference": the UNMODIFIED reference (drin/model.py, common/utils.py TripletLoss, torch.optim.Adam -- the body of
+    train.py:32-34,55-56) imported from oracle/_ref (staged by oracle/make_ref.py) or /root/reference;
+    kind "port": the oracle restatement (loops=True keeps the reference's per-item Python loops).
+    "auto" takes the reference when it is importable."""
     import torch
     from drin_b200.synthetic import make_batch
     from oracle import drin_oracle as O
+    from oracle import ref_import
 
     torch.set_num_threads(os.cpu_count() or 1)
     cands = 10 if dataset == "wikidiverse" else 100
-    cfg = O.DrinConfig(num_candidates_model=cands + 1, gcn_edge_feature=edge_feature)
     b = make_batch(dataset, batch, 0, cands)
-    sd = O.init_state(cfg, 0)
-    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    opt = torch.optim.Adam(list(leaves.values()), lr=1e-3)
-    loss_fn = O.triplet_loss_loops if loops else O.triplet_loss
+    if kind == "auto":
+        kind = "reference" if ref_import.available() else "port"
+    if kind == "reference":
+        m, u, a = ref_import.load(dataset, cands, 64, gcn_edge_feature=edge_feature)
+        torch.manual_seed(0)
+        model = m.Model()
+        loss_obj = u.TripletLoss(a.triplet_margin)
+        opt = torch.optim.Adam(model.parameters(), lr=a.learning_rate)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        s = O.forward(leaves, b[:-1], cfg, loops)
-        loss = loss_fn(b[-1], s, cfg.triplet_margin)
-        loss.backward()
-        opt.step()
-        return float(loss)
+        def step():
+            y_hat = model(b[:-1])                       # train.py:32-34
+            loss = loss_obj(b[-1], y_hat)
+            opt.zero_grad(set_to_none=True)             # Lightning's automatic optimisation
+            loss.backward()
+            opt.step()
+            return float(loss)                          # train.py:35
 
-    def rank():
-        with torch.no_grad():
-            return O.forward(leaves, b[:-1], cfg, loops)
+        def rank():
+            with torch.no_grad():
+                return model(b[:-1])
+    else:
+        cfg = O.DrinConfig(num_candidates_model=cands + 1, gcn_edge_feature=edge_feature)
+        sd = O.init_state(cfg, 0)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.Adam(list(leaves.values()), lr=1e-3)
+        loss_fn = O.triplet_loss_loops if loops else O.triplet_loss
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            s = O.forward(leaves, b[:-1], cfg, loops)
+            loss = loss_fn(b[-1], s, cfg.triplet_margin)
+            loss.backward()
+            opt.step()
+            return float(loss)
+
+        def rank():
+            with torch.no_grad():
+                return O.forward(leaves, b[:-1], cfg, loops)
 
     for _ in range(warmup):
         step()
@@ -153,7 +181,7 @@ def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="s
         rank()
     t_rank = (time.perf_counter() - t0) / max(steps // 2, 1)
     return dict(train_mps=batch / t_train, rank_mps=batch / t_rank, ms_per_step=t_train * 1e3, cores=os.cpu_count(),
-                threads=torch.get_num_threads())
+                threads=torch.get_num_threads(), kind=kind)
 
 
 def run_reference(args):
@@ -163,16 +191,17 @@ def run_reference(args):
     B = args.cpu_batch if args.cpu_batch else 512
     r = cpu_reference_run(args.dataset, B, args.steps, args.warmup, loops=True, edge_feature=args.edge_feature)
     cands = 10 if args.dataset == "wikidiverse" else 100
-    sample = (f"oracle port of the reference (per-item Python loops kept), {args.dataset}-shaped batch of {B} mentions per "
-              f"step, fwd+TripletLoss+bwd+Adam, {args.warmup} warm-up + {args.steps} timed steps, torch CPU "
-              f"{r['threads']} threads")
+    what = ("the UNMODIFIED reference (drin/model.py + common/utils.py TripletLoss + torch Adam, staged under oracle/_ref)"
+            if r["kind"] == "reference" else "oracle port of the reference (per-item Python loops kept)")
+    sample = (f"{what}, {args.dataset}-shaped batch of {B} mentions per step, fwd+TripletLoss+bwd+Adam, "
+              f"{args.warmup} warm-up + {args.steps} timed steps, torch CPU {r['threads']} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["train_mps"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"DRIN train step, {args.dataset}-shaped synthetic features, C={cands + 1}",
                    "batch_per_step": B, "parallelism": "host CPU"},
-        "cpu_baseline": {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["train_mps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ranking": {"value": r["rank_mps"], "unit": UNIT},
         "gpu_launches": 0,
@@ -400,9 +429,11 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.dataset, args.cpu_batch, 12, 2, loops=True, edge_feature=args.edge_feature)
-        rv = cpu_reference_run(args.dataset, args.cpu_batch, 6, 1, loops=False, edge_feature=args.edge_feature)
-        cpu = {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": (f"oracle port (reference-style Python loops), {args.dataset}-shaped batch of {args.cpu_batch}, "
+        rv = cpu_reference_run(args.dataset, args.cpu_batch, 6, 1, loops=False, edge_feature=args.edge_feature, kind="port")
+        cpu = {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": (("the unmodified reference (oracle/_ref)" if r["kind"] == "reference" else
+                           "oracle port (reference-style Python loops)") +
+                          f", {args.dataset}-shaped batch of {args.cpu_batch}, "
                           f"fwd+loss+bwd+Adam, 2 warm-up + 12 timed steps, {r['threads']} torch threads"),
                "ranking_value": r["rank_mps"], "vectorised_port_value": rv["train_mps"]}
 

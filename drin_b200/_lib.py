@@ -59,11 +59,13 @@ def load():
         if override:
             path = override
         elif not _build.is_fresh():
-            try:
-                _build.build()
-            except Exception as e:  # no nvcc on the box: use the shipped .so if there is one
-                if not os.path.exists(path):
-                    raise RuntimeError(f"libdrin_b200.so is missing and could not be built: {e}") from e
+            if _build.have_nvcc():
+                _build.build()          # a compile / link error after a source edit must surface, never a stale library
+            elif not os.path.exists(path):
+                raise RuntimeError("libdrin_b200.so is missing and there is no nvcc to build it")
+            else:
+                import warnings
+                warnings.warn("libdrin_b200.so does not match the sources and nvcc is absent: using the shipped library")
         lib = C.CDLL(path)
         lib.drin_last_error.restype = C.c_char_p
         # the ctypes mirrors above must match the structs the library was compiled with

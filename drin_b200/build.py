@@ -28,6 +28,10 @@ def _nvcc() -> str:
     return nvcc
 
 
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

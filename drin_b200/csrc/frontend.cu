@@ -368,7 +368,10 @@ int frontend(cudaStream_t stream, const FrontendArgs& a, bool bf16_features) {
     return fail(DRIN_ERR_ARG, "frontend: built for bert_embed_dim 768 / resnet_embed_dim 2048 (got %d / %d)", a.D, a.R);
   if (a.Om > FE_MAX_OM) return fail(DRIN_ERR_ARG, "frontend: at most %d mention objects", FE_MAX_OM);
   if (a.B <= 0 || a.C <= 0) return fail(DRIN_ERR_ARG, "frontend: empty batch");
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int dev = 0;
+  DRIN_CUDA(cudaGetDevice(&dev));
+  bool& attr_set = attr_set_dev[dev & 63];         // function attributes are per device
   if (!attr_set) {
     const int max_smem = 100 * 1024;
     DRIN_CUDA(cudaFuncSetAttribute(frontend_kernel<float, 4, 768, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

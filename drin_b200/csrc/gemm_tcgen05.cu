@@ -595,8 +595,16 @@ void gemm_debug_set_mn_desc(int lbo_bytes, int sbo_bytes) {
   g_mn_sbo = sbo_bytes;
 }
 
-static int g_num_sms = 0;
-static int* g_error_flag = nullptr;
+// Per-device state: one process may drive several GPUs (function attributes, the SM count and the device-side
+// error flag all belong to the device that was current when they were set up).
+constexpr int MAX_DEVICES = 64;
+struct GemmDeviceState {
+  int status = -1;
+  int num_sms = 0;
+  int* error_flag = nullptr;
+};
+static GemmDeviceState g_dev[MAX_DEVICES];
+static std::mutex g_dev_mutex;
 static bool g_force_1cta = false;
 
 template <bool A_MN, bool B_MN, int CTAS>
@@ -617,12 +625,15 @@ static cudaError_t launch_gemm(int grid, cudaStream_t stream, const CUtensorMap&
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<A_MN, B_MN, CTAS>, tA0, tA1, tB0, tB1, p);
 }
 
-static int gemm_init_once() {
-  static int status = -1;
-  if (status >= 0) return status;
+static int gemm_init_device(GemmDeviceState** out) {
   int dev = 0;
   DRIN_CUDA(cudaGetDevice(&dev));
-  DRIN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(DRIN_ERR_ARG, "gemm: device ordinal %d out of range", dev);
+  GemmDeviceState& st = g_dev[dev];
+  *out = &st;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (st.status >= 0) return st.status;
+  DRIN_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
 #define DRIN_GEMM_ATTR(A, B, C)                                                                               \
   DRIN_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  SMEM_TOTAL_BYTES))
@@ -637,16 +648,18 @@ static int gemm_init_once() {
     const char* e = getenv("DRIN_GEMM_1CTA");
     g_force_1cta = e && e[0] == '1';
   }
-  DRIN_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
-  DRIN_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
-  status = DRIN_OK;
-  return status;
+  DRIN_CUDA(cudaMalloc(&st.error_flag, sizeof(int)));
+  DRIN_CUDA(cudaMemset(st.error_flag, 0, sizeof(int)));
+  st.status = DRIN_OK;
+  return st.status;
 }
 
 int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const Operand& B, long long M, int N,
                  long long K, const GemmEpilogue& ep, int ksplit, float* partial, SplitKJobs* defer) {
   prof::Scope prof_scope(stream, prof::GEMM, 2.0 * (double)M * (double)N * (double)K, 0);
-  DRIN_TRY(gemm_init_once());
+  GemmDeviceState* dstate = nullptr;
+  DRIN_TRY(gemm_init_device(&dstate));
+  const int g_num_sms = dstate->num_sms;
   if (M <= 0 || N <= 0 || K <= 0) return fail(DRIN_ERR_ARG, "gemm: empty problem M=%lld N=%d K=%lld", M, N, K);
   const int planes = A.lo ? 2 : 1;
   if ((A.lo != nullptr) != (B.lo != nullptr)) return fail(DRIN_ERR_ARG, "gemm: A and B must have the same planes");
@@ -697,7 +710,7 @@ int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const
   p.ld_planes = ep.ld_planes;
   p.mn_lbo = g_mn_lbo ? (uint32_t)g_mn_lbo : (uint32_t)(BK * 128);
   p.mn_sbo = g_mn_sbo ? (uint32_t)g_mn_sbo : 1024u;
-  p.error_flag = g_error_flag;
+  p.error_flag = dstate->error_flag;
   if (ksplit > 1) {
     if (!partial || !ep.C || ep.out_hi || (N % 4))
       return fail(DRIN_ERR_ARG, "gemm: split-K needs a partial buffer, an fp32 output with N %% 4 == 0 and no planes");

@@ -261,8 +261,13 @@ int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* 
 
 // TopkAccuracy.update: gold is a hit for k when fewer than k real candidates score strictly higher
 // (equivalent to gold >= k-th largest, ties count as hits).
+struct TopkList {      // the k values travel by value in the launch parameters: no device buffer, no host copy to order
+  int k[16];
+};
+
 __global__ void topk_hits_kernel(const float* __restrict__ s, const unsigned char* __restrict__ y, int B, int C,
-                                 const int* __restrict__ topk, int nk, unsigned long long* __restrict__ hits) {
+                                 const TopkList topk_list, int nk, unsigned long long* __restrict__ hits) {
+  const int* topk = topk_list.k;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   for (int g = 0; g < C - 1; ++g) {
@@ -279,10 +284,9 @@ __global__ void topk_hits_kernel(const float* __restrict__ s, const unsigned cha
 int topk_hits(cudaStream_t stream, const float* scores, const unsigned char* labels, int B, int C, const int* topk,
               int nk, long long* hits) {
   if (nk <= 0 || nk > 16) return fail(DRIN_ERR_ARG, "topk_hits: 1..16 values of k");
-  static int* d_topk = nullptr;
-  if (!d_topk) DRIN_CUDA(cudaMalloc(&d_topk, 16 * sizeof(int)));
-  DRIN_CUDA(cudaMemcpyAsync(d_topk, topk, nk * sizeof(int), cudaMemcpyHostToDevice, stream));
-  topk_hits_kernel<<<(B + 127) / 128, 128, 0, stream>>>(scores, labels, B, C, d_topk, nk,
+  TopkList list{};
+  for (int j = 0; j < nk; ++j) list.k[j] = topk[j];
+  topk_hits_kernel<<<(B + 127) / 128, 128, 0, stream>>>(scores, labels, B, C, list, nk,
                                                         reinterpret_cast<unsigned long long*>(hits));
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;

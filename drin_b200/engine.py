@@ -6,6 +6,7 @@ PyTorch is plumbing here (device memory, streams); all arithmetic happens in lib
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -187,8 +188,84 @@ def inspect_batch(batch: Sequence[torch.Tensor], num_candidates_model: Optional[
     return Problem(B, Cc, Lm, Le, P, Om, Oe, D, R, BF16 if feat_dtype == torch.bfloat16 else FP32)
 
 
+class _Lease:
+    """Ownership of one pooled workspace by one forward call.  ``live``: saved activations are still needed;
+    ``done``: a backward has run (the workspace may be taken over by a later forward, which bumps its generation so
+    that a second backward through this lease fails loudly instead of reading overwritten activations)."""
+    __slots__ = ("entry", "gen", "state", "__weakref__")
+
+    def __init__(self, entry, gen):
+        self.entry, self.gen, self.state = entry, gen, "live"
+
+    def valid(self) -> bool:
+        return self.state != "released" and self.entry["gen"] == self.gen
+
+    def release(self) -> None:
+        if self.valid():
+            self.entry["lease"] = None
+        self.state = "released"
+
+
+class WorkspacePool:
+    """Workspaces of one Engine.  Every training forward owns its workspace until its backward has run (or its
+    autograd graph is freed), so ``loss(model(b1)) + loss(model(b2))`` or a no_grad validation forward between
+    forward and backward work like they do with the reference module; the steady state of a train loop is still
+    ONE workspace (a finished lease is reclaimed by the next forward)."""
+
+    def __init__(self):
+        self.entries: List[dict] = []
+
+    def _lease_of(self, e) -> Optional[_Lease]:
+        ref = e["lease"]
+        lease = ref() if ref is not None else None
+        if lease is None or lease.state == "released" or lease.gen != e["gen"]:
+            e["lease"] = None
+            return None
+        return lease
+
+    def acquire(self, need: int, device) -> _Lease:
+        mine = [e for e in self.entries if e["ws"].device == device]
+        free = [e for e in mine if self._lease_of(e) is None]
+        fit = sorted((e for e in free if e["ws"].numel() >= need), key=lambda e: e["ws"].numel())
+        if fit:
+            e = fit[0]
+        else:
+            done = sorted((e for e in mine if e not in free and self._lease_of(e).state == "done"
+                           and e["ws"].numel() >= need), key=lambda e: e["ws"].numel())
+            if done:
+                e = done[0]
+            else:
+                for old in free:                       # too small and unowned: let the allocator have it back
+                    self.entries.remove(old)
+                e = dict(ws=torch.empty(need, dtype=torch.uint8, device=device), gen=0, lease=None)
+                self.entries.append(e)
+        e["gen"] += 1
+        lease = _Lease(e, e["gen"])
+        e["lease"] = weakref.ref(lease)
+        return lease
+
+    def tensors(self) -> List[torch.Tensor]:
+        return [e["ws"] for e in self.entries]
+
+
+class ForwardCtx:
+    """State of one forward call: problem, config struct, workspace and its lease.  Unpacks like the former
+    ``(pb, cfg, ws)`` tuple."""
+    __slots__ = ("pb", "cfg", "ws", "lease")
+
+    def __init__(self, pb, cfg, ws, lease):
+        self.pb, self.cfg, self.ws, self.lease = pb, cfg, ws, lease
+
+    def __iter__(self):
+        return iter((self.pb, self.cfg, self.ws))
+
+    def release(self) -> None:
+        """The saved activations are no longer needed (called by Trainer after backward)."""
+        self.lease.release()
+
+
 class Engine:
-    """One instance per module: caches the workspace and marshals calls into the C ABI."""
+    """One instance per module: owns the workspace pool and marshals calls into the C ABI."""
 
     def __init__(self, num_layers: int, edge_enabled: Sequence[float] = (1, 1, 1, 1), static_edges: bool = False,
                  vector_edges: bool = False):
@@ -199,7 +276,7 @@ class Engine:
         self.edge_enabled = tuple(float(x) for x in edge_enabled)
         if len(self.edge_enabled) != 4:
             raise ValueError("gcn_edge_enabled must have 4 entries")
-        self._ws: Optional[torch.Tensor] = None
+        self.pool = WorkspacePool()
 
     # ---- struct marshalling -----------------------------------------------------------------
     def config(self, pb: Problem, training: bool, indexed: bool = False) -> _lib.DrinConfig:
@@ -256,12 +333,8 @@ class Engine:
         _lib.check(self.lib.drin_workspace_bytes(C.byref(cfg), C.byref(n)), "drin_workspace_bytes")
         return n.value
 
-    def workspace(self, cfg, device) -> torch.Tensor:
-        need = self.workspace_bytes(cfg)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
+    def workspace(self, cfg, device) -> _Lease:
+        return self.pool.acquire(self.workspace_bytes(cfg), device)
 
     # ---- calls ------------------------------------------------------------------------------
     def forward(self, batch, params: Dict[str, torch.Tensor], training: bool,
@@ -279,21 +352,32 @@ class Engine:
             dev = batch[0].device
         cfg = self.config(pb, training, indexed)
         with torch.cuda.device(dev):
-            ws = self.workspace(cfg, dev)
+            lease = self.workspace(cfg, dev)
+            ws = lease.entry["ws"]
             scores = torch.empty(pb.B, pb.C, dtype=torch.float32, device=dev)
             ins = self.inputs(batch)
             ps = self.params(params, pb.D, pb.R)
-            _lib.check(self.lib.drin_forward(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
-                                             C.c_size_t(ws.numel()), _ptr(scores), _stream()), "drin_forward")
-        return scores, (pb, cfg, ws)
+            try:
+                _lib.check(self.lib.drin_forward(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
+                                                 C.c_size_t(ws.numel()), _ptr(scores), _stream()), "drin_forward")
+            except Exception:
+                lease.release()
+                raise
+        if not training:
+            lease.release()        # nothing is saved: the next call on this stream may reuse the memory
+        return scores, ForwardCtx(pb, cfg, ws, lease)
 
     def backward(self, ctx, batch, params, dscores: torch.Tensor, grads: Dict[str, torch.Tensor],
                  layers_done: Optional[torch.cuda.Event] = None) -> None:
         """layers_done: optional event recorded on the current stream once every GCN-layer and bias gradient is final
         (only the four input-projection weight gradients still follow)."""
         pb, cfg, ws = ctx
-        if ws is not self._ws:
-            raise RuntimeError("workspace was re-planned between forward and backward")
+        if not cfg.training:
+            raise RuntimeError("backward needs a forward with training=True (activations were not saved)")
+        if not ctx.lease.valid():
+            raise RuntimeError("the activations of this forward are gone: its workspace was released or taken over by a "
+                               "later forward after a first backward (a second backward through the same graph is only "
+                               "possible when no other forward ran in between)")
         dscores = dscores.contiguous()
         with torch.cuda.device(dscores.device):
             ins = self.inputs(batch)
@@ -303,6 +387,7 @@ class Engine:
             _lib.check(self.lib.drin_backward_ex(C.byref(cfg), C.byref(ins), C.byref(ps), _ptr(ws),
                                                  C.c_size_t(ws.numel()), _ptr(dscores), C.byref(gs), ev, _stream()),
                        "drin_backward")
+        ctx.lease.state = "done"
 
     def debug_buffer(self, ctx, name: str, layer: int = 0) -> torch.Tensor:
         """Copy of a named fp32 intermediate of the last forward (tests only)."""

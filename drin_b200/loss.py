@@ -23,19 +23,26 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-_scratch = {}
+_scratch = {}          # (B, C, device) -> scratch tensor; a few shapes alternate in practice (train / eval / last batch)
+_SCRATCH_KEEP = 8
 
 
 def _loss_scratch(B: int, Cn: int, device) -> torch.Tensor:
     key = (B, Cn, str(device))
-    t = _scratch.get(key)
+    t = _scratch.pop(key, None)
     if t is None:
         n = C.c_size_t(0)
         _lib.check(_lib.load().drin_loss_scratch_bytes(C.c_int32(B), C.c_int32(Cn), C.byref(n)), "drin_loss_scratch_bytes")
         t = torch.empty(n.value, dtype=torch.uint8, device=device)
-        _scratch.clear()
-        _scratch[key] = t
+        while len(_scratch) >= _SCRATCH_KEEP:         # least recently used first (dicts keep insertion order)
+            _scratch.pop(next(iter(_scratch)))
+    _scratch[key] = t                                 # most recently used last
     return t
+
+
+def scratch_tensors():
+    """The cached scratch buffers (a CUDA graph that captured the loss keeps references to them)."""
+    return list(_scratch.values())
 
 
 def triplet_loss_sharded(scores_all: torch.Tensor, labels_all: torch.Tensor, margin: float, row_offset: int = 0,

@@ -20,8 +20,36 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros_like(flat)
         self.skip = model.dead_mask()      # parameters whose grad is None upstream are never stepped
 
+    def _collect_autograd_grads(self) -> None:
+        """``Model.forward`` + ``loss.backward()`` (the reference's Lightning flow, train.py:46-56) leaves the gradients
+        in ``p.grad``, not in the flat buffer the kernel reads (only ``Trainer`` writes that one directly): copy them in.
+        Parameters whose grad is None must be exactly the reference's dead ones (they are masked out of the update)."""
+        m = self.model
+        views, dead, found = m._grad_views(), set(m._dead), False
+        for name, p in m.named_parameters():
+            if p.grad is None:
+                if name not in dead:
+                    raise RuntimeError(f"FusedAdam.step(): parameter {name} has no gradient -- run backward first "
+                                       "(frozen parameters are not supported)")
+                continue
+            found = True
+            if p.grad.data_ptr() != views[name].data_ptr():
+                views[name].copy_(p.grad)
+        if not found:
+            raise RuntimeError("FusedAdam.step(): no gradients -- neither Trainer.forward_backward nor loss.backward() ran")
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        self.model._flat_grads_valid = False
+        for p in self.model.parameters():
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
     def step(self) -> None:
         m = self.model
+        if not getattr(m, "_flat_grads_valid", False):
+            self._collect_autograd_grads()
         flat, grad = m.flat_params, m.flat_grads
         if self.exp_avg.device != flat.device:
             raise RuntimeError("model moved after the optimizer was built")

@@ -96,8 +96,10 @@ class Trainer:
         if _dist_on(self.group) and self.overlap_allreduce:
             return self._backward_overlapped(ctx, inputs, params, dscores, loss)
         m._engine.backward(ctx, inputs, params, dscores, m._grad_views())
+        ctx.release()
         # 31.5 MB of gradients + this rank's share of the loss in the bucket's tail
         loss = reduce_grads_and_loss(m.flat_grads_bucket, m.flat_params.numel(), loss, self.group)
+        m._flat_grads_valid = True          # FusedAdam reads the flat buffer directly
         return loss.reshape(())
 
     def _backward_overlapped(self, ctx, inputs, params, dscores, loss_share) -> torch.Tensor:
@@ -112,11 +114,13 @@ class Trainer:
         bucket, n, off = m.flat_grads_bucket, m.flat_params.numel(), m.layer_grad_offset()
         bucket[n:n + 1].copy_(loss_share.reshape(1))      # before backward: covered by the layers-done event
         m._engine.backward(ctx, inputs, params, dscores, m._grad_views(), layers_done=self._layers_done)
+        ctx.release()
         self._comm_stream.wait_event(self._layers_done)
         with torch.cuda.stream(self._comm_stream):
             work = dist.all_reduce(bucket[off:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         dist.all_reduce(bucket[:off], op=dist.ReduceOp.SUM, group=self.group)
         work.wait()                                       # the current stream waits for the side-stream collective
+        m._flat_grads_valid = True
         return bucket[n:n + 1].clone().reshape(())
 
     def step(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -221,6 +225,7 @@ class GraphedStoreStep:
         dev = store.device
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self._host_idx = torch.zeros(self.B, dtype=torch.int64).pin_memory()
+        self._idx_copied: Optional[torch.cuda.Event] = None
         # optimizer / parameter state is advanced by warm-up and capture runs: snapshot and restore it
         opt, m = trainer.opt, trainer.model
         saved = (m.flat_params.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt._step.clone())
@@ -235,6 +240,10 @@ class GraphedStoreStep:
         with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
             self.loss = trainer.step(store.select(self.idx))
             self.scores = trainer.last_scores
+        # the graph has raw pointers into the engine's workspace(s) and the loss scratch baked in: keep them alive for
+        # as long as the graph exists, whatever other batch sizes the engine or the loss see in between
+        from .loss import scratch_tensors
+        self._keep = list(m._engine.pool.tensors()) + scratch_tensors() + [m.flat_grads_bucket, store]
         with torch.no_grad():
             m.flat_params.copy_(saved[0])
             opt.exp_avg.copy_(saved[1])
@@ -251,8 +260,13 @@ class GraphedStoreStep:
         else:
             if int(idx.min()) < 0 or int(idx.max()) >= len(self.store):
                 raise IndexError("mention index out of range")
+            if self._idx_copied is not None:
+                self._idx_copied.synchronize()          # the previous step's async copy has read the pinned buffer
             self._host_idx.copy_(idx)
             self.idx.copy_(self._host_idx, non_blocking=True)
+            if self._idx_copied is None:
+                self._idx_copied = torch.cuda.Event()
+            self._idx_copied.record()
         self.graph.replay()
         return self.loss
 
@@ -296,6 +310,8 @@ class HostFeeder:
         sid = self.next_slot
         self.next_slot = (self.next_slot + 1) % len(self.slots)
         slot = self.slots[sid]
+        if slot.get("ready") is not None:
+            slot["ready"].synchronize()        # the slot's previous async copy has read its pinned staging buffers
         srcs = list(host_batch)
         mtf, start, end = srcs[0], srcs[2], srcs[3]
         Lm = mtf.shape[1]

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference (starreeze/drin) in the build container -- TEST INFRASTRUCTURE.
+"""Import the UNMODIFIED reference (starreeze/drin) -- TEST / BASELINE INFRASTRUCTURE.
 
-``/root/reference`` exists only in the build container, never on the GPU box: this module is used
-solely by ``oracle/make_golden.py`` (golden-vector generation) and by CPU tests that skip when the
-reference tree is absent.  Recipe from SURVEY.md section 8(c):
+``/root/reference`` exists only in the build container, never on the GPU box; ``oracle/_ref/`` is the staged copy of
+the four files of the path (``oracle/make_ref.py``; git-ignored, travels with gpurun).  Used by
+``oracle/make_golden.py`` (golden-vector generation), by tests that skip when neither tree is present and by
+``bench.py``'s CPU reference legs.  Recipe from SURVEY.md section 8(c):
   * ``common.args`` is patched BEFORE any model module is imported (consumers star-import it, so the
     values are copied at import time);
   * ``torchmetrics`` (absent from this image) is stubbed with a 6-line ``Metric``;
@@ -16,7 +17,15 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("DRIN_REFERENCE_ROOT", "/root/reference")
+def _find_root() -> str:
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for root in (os.environ.get("DRIN_REFERENCE_ROOT"), "/root/reference", staged):
+        if root and os.path.isfile(os.path.join(root, "drin", "model.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

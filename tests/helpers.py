@@ -45,3 +45,41 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b|  (tensor-wise relative error used for the 1e-4 fp32 bar)."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def elementwise_violations(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4) -> int:
+    """Element-wise bar next to the norm-wise ``rel_err``: every entry must satisfy
+    ``|a - b| <= tol * |b| + tol * rms(b)`` (the rms floor keeps entries that are tiny next to their tensor's scale,
+    whose last bits are fp32 re-association noise, from dominating).  Returns the number of violating entries."""
+    a, b = a.double(), b.double()
+    rms = b.pow(2).mean().sqrt()
+    return int(((a - b).abs() > tol * b.abs() + tol * rms).sum())
+
+
+def assert_rankings_consistent(scores: torch.Tensor, ref: torch.Tensor, labels: torch.Tensor, top_k, tol: float = 1e-4):
+    """Tie-tolerant ranking parity at scale (scores [B, C] incl. the gold slot, ranking over [:, :-1] like
+    common/utils.py:60-66):
+      * every pair of candidates our scores order differently from the reference has a reference gap < tol;
+      * top-k hit flags (gold score >= k-th largest, ties are hits) agree on every row whose reference gold score is
+        further than tol from the reference's k-th largest.
+    Returns (inverted pairs, largest inverted reference gap, rows compared per k)."""
+    s, r = scores.double()[:, :-1], ref.double()[:, :-1]
+    d_s = s.unsqueeze(2) - s.unsqueeze(1)
+    d_r = r.unsqueeze(2) - r.unsqueeze(1)
+    inverted = (d_s > 0) & (d_r < 0)
+    worst = float((-d_r[inverted]).max()) if bool(inverted.any()) else 0.0
+    assert worst < tol, f"a candidate pair with reference gap {worst:.3e} is ordered differently"
+    y = labels.bool()
+    has_gold = y.any(dim=1)
+    compared = {}
+    for k in top_k:
+        if k > s.shape[1]:
+            continue
+        kth_s = torch.topk(s, k, dim=1).values[:, -1]
+        kth_r = torch.topk(r, k, dim=1).values[:, -1]
+        gold_s = (s * y).sum(1)
+        gold_r = (r * y).sum(1)
+        clear = has_gold & ((gold_r - kth_r).abs() > tol)
+        assert torch.equal((gold_s >= kth_s)[clear], (gold_r >= kth_r)[clear]), f"top-{k} hits differ on clear rows"
+        compared[k] = int(clear.sum())
+    return int(inverted.sum()), worst, compared

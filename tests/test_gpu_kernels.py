@@ -190,6 +190,7 @@ def test_fused_adam_matches_torch_adam():
     for step in range(3):
         g = torch.randn_like(model.flat_params) * (10.0 ** (-step))
         model.flat_grads.copy_(g)
+        model._flat_grads_valid = True          # what Trainer.forward_backward sets after writing the flat buffer
         for n, r, (o, cnt, shape) in zip(names, ref, [model._offsets[n] for n in names]):
             r.grad = None if n in dead else g[o:o + cnt].view(shape).clone()
         opt.step()
