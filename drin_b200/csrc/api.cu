@@ -137,7 +137,24 @@ int drin_debug_option(const char* name, int32_t value) {
   else if (!strcmp(name, "row_slice_min")) debug_set_row_slice_min(value);
   else if (!strcmp(name, "vec_bwd_width")) debug_set_vec_bwd_width(value);
   else if (!strcmp(name, "vec_ctas_per_sm")) debug_set_vec_ctas_per_sm(value);
+  else if (!strcmp(name, "gemm_sm_cap")) debug_set_gemm_sm_cap(value);
+  else if (!strcmp(name, "workspace_guard")) debug_set_workspace_guard(value);
   else return fail(DRIN_ERR_ARG, "drin_debug_option: unknown option '%s'", name);
+  return DRIN_OK;
+}
+
+// Test hook: byte offsets of the guard bands of the workspace plan for cfg (see "workspace_guard"); each band is
+// *guard_bytes long.  offsets may be NULL to query the count.
+int drin_debug_guard_regions(const drin_config* cfg, size_t* offsets, int32_t max_regions, int32_t* count,
+                             size_t* guard_bytes) {
+  if (!cfg || !count || !guard_bytes) return fail(DRIN_ERR_ARG, "drin_debug_guard_regions: null argument");
+  Workspace ws;
+  DRIN_TRY(plan_workspace(*cfg, nullptr, nullptr, ws));
+  const std::vector<size_t>& g = debug_workspace_guard_offsets();
+  *count = (int32_t)g.size();
+  *guard_bytes = debug_workspace_guard_bytes();
+  if (offsets)
+    for (int i = 0; i < (int)g.size() && i < max_regions; ++i) offsets[i] = g[i];
   return DRIN_OK;
 }
 

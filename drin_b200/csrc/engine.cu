@@ -1,6 +1,8 @@
 // Workspace plan + forward orchestration of the DRIN hot path (reference drin/model.py:164-209).
 #include "engine.cuh"
 
+#include <vector>
+
 namespace drin {
 
 int check_config(const drin_config& c) {
@@ -14,16 +16,31 @@ int check_config(const drin_config& c) {
   return DRIN_OK;
 }
 
+// Test hook (no compute-sanitizer on the GPU pool): with a guard size set, every buffer of the workspace plan is
+// followed by `guard` bytes that no kernel may touch.  A test fills the whole workspace with a poison pattern, runs a
+// step and checks (a) every guard band still holds the pattern (no out-of-bounds write between buffers), (b) results
+// equal those of a zero-filled workspace bit for bit (no read of memory the step did not write itself).
+static size_t g_guard_bytes = 0;
+static std::vector<size_t> g_guard_offsets;      // of the most recent plan (planning is host-side and cheap)
+void debug_set_workspace_guard(int bytes) { g_guard_bytes = bytes > 0 ? align_up((size_t)bytes, 256) : 0; }
+size_t debug_workspace_guard_bytes() { return g_guard_bytes; }
+const std::vector<size_t>& debug_workspace_guard_offsets() { return g_guard_offsets; }
+
 namespace {
 struct Bump {
   char* base;
   size_t off = 0;
-  explicit Bump(void* b) : base(static_cast<char*>(b)) {}
+  explicit Bump(void* b) : base(static_cast<char*>(b)) { g_guard_offsets.clear(); }
   template <typename T>
   T* take(size_t n) {
     off = align_up(off, 256);
     T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
     off += n * sizeof(T);
+    if (g_guard_bytes) {
+      off = align_up(off, 256);
+      g_guard_offsets.push_back(off);
+      off += g_guard_bytes;
+    }
     return p;
   }
   Planes planes(size_t n, bool split) {

@@ -1,5 +1,6 @@
 // Workspace plan and forward/backward orchestration of the DRIN hot path.
 #pragma once
+#include <vector>
 #include "../../include/drin_b200.h"
 #include "kernels.cuh"
 
@@ -93,6 +94,9 @@ inline bool vector_path(const drin_config& c) { return c.vector_edges && !c.stat
 int check_config(const drin_config& c);
 // Carve `base` (may be null: size query) into the buffers above.
 int plan_workspace(const drin_config& c, const drin_inputs* in, void* base, Workspace& ws);
+void debug_set_workspace_guard(int bytes);
+size_t debug_workspace_guard_bytes();
+const std::vector<size_t>& debug_workspace_guard_offsets();
 
 int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace, size_t workspace_bytes,
             float* scores, cudaStream_t stream);

@@ -606,6 +606,9 @@ struct GemmDeviceState {
 static GemmDeviceState g_dev[MAX_DEVICES];
 static std::mutex g_dev_mutex;
 static bool g_force_1cta = false;
+static int g_sm_cap = 0;      // > 0: persistent GEMM grids use at most this many SMs (the rest stay free for kernels of a
+                              // concurrent stream); 0 = all
+void debug_set_gemm_sm_cap(int v) { g_sm_cap = v > 0 ? v : 0; }
 
 template <bool A_MN, bool B_MN, int CTAS>
 static cudaError_t launch_gemm(int grid, cudaStream_t stream, const CUtensorMap& tA0, const CUtensorMap& tA1,
@@ -721,7 +724,8 @@ int gemm_tcgen05(cudaStream_t stream, GemmLayout layout, const Operand& A, const
     p.c_split_stride = 0;
   }
   const long long tiles = (long long)p.m_tiles * p.n_tiles * ksplit;
-  const int workers = g_num_sms / ctas;
+  const int usable_sms = (g_sm_cap > 0 && g_sm_cap < g_num_sms) ? g_sm_cap : g_num_sms;
+  const int workers = usable_sms / ctas > 0 ? usable_sms / ctas : 1;
   const int grid = ctas * (int)(tiles < workers ? tiles : workers);
   cudaError_t le;
   if (ctas == 1) {

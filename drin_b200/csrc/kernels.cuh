@@ -206,6 +206,7 @@ int wm_fixup(cudaStream_t stream, const float* dwa, const float* dwb, const floa
              const float* w_m, int D, float* dw_m, float* db_u, float* db_v);
 void debug_set_vec_bwd_width(int v);
 void debug_set_vec_ctas_per_sm(int v);
+void debug_set_gemm_sm_cap(int v);
 int vec_layer_fwd(cudaStream_t stream, const VecLayerArgs& a);
 int vec_layer_bwd(cudaStream_t stream, const VecLayerArgs& a, int* partial_rows);
 int vec_layer_ctas();

@@ -207,6 +207,13 @@ int drin_debug_buffer(const drin_config* cfg, void* workspace, const char* name,
  * (upper bound on the resident-CTA grid of the vector-edge kernels, 0 = all).  Not part of the drop-in surface. */
 int drin_debug_option(const char* name, int32_t value);
 
+/* Test hook (the GPU pool has no compute-sanitizer): with drin_debug_option("workspace_guard", n) every buffer of the
+ * workspace plan is followed by n bytes (rounded up to 256) no kernel may touch.  Returns the byte offsets of those
+ * guard bands for cfg (offsets may be NULL to query *count); a test poisons the workspace, runs a step and checks the
+ * bands.  "gemm_sm_cap" (debug option): upper bound on the SMs a persistent GEMM grid uses, 0 = all. */
+int drin_debug_guard_regions(const drin_config* cfg, size_t* offsets, int32_t max_regions, int32_t* count,
+                             size_t* guard_bytes);
+
 #ifdef __cplusplus
 }
 #endif

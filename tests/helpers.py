@@ -47,13 +47,31 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def elementwise_floor(b: torch.Tensor) -> torch.Tensor:
+    """Per-entry scale for the element-wise bar.  Vectors: rms(b).  Matrices (weight gradients dW = sum_r dh_r z_r^T):
+    max(rms(b), sqrt(rowrms_i(b) * colrms_j(b))) -- an entry of an outer-product sum carries rounding noise in proportion
+    to the norms of ITS row of dh and column of z, not to its own (possibly cancelled) value or to the tensor-wide rms;
+    weight gradients here are heavy-tailed (rms / max = 0.07-0.12 for w_h), so a flat rms floor misjudges exactly the
+    entries in outlier rows / columns."""
+    b = b.double()
+    rms = b.pow(2).mean().sqrt()
+    if b.dim() != 2:
+        return rms.expand_as(b)
+    row = b.pow(2).mean(dim=1, keepdim=True).sqrt()
+    col = b.pow(2).mean(dim=0, keepdim=True).sqrt()
+    return torch.maximum((row * col).sqrt(), rms.expand_as(b))
+
+
+def elementwise_ratio(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4) -> torch.Tensor:
+    a, b = a.double(), b.double()
+    return (a - b).abs() / (tol * b.abs() + tol * elementwise_floor(b))
+
+
 def elementwise_violations(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4) -> int:
     """Element-wise bar next to the norm-wise ``rel_err``: every entry must satisfy
-    ``|a - b| <= tol * |b| + tol * rms(b)`` (the rms floor keeps entries that are tiny next to their tensor's scale,
-    whose last bits are fp32 re-association noise, from dominating).  Returns the number of violating entries."""
-    a, b = a.double(), b.double()
-    rms = b.pow(2).mean().sqrt()
-    return int(((a - b).abs() > tol * b.abs() + tol * rms).sum())
+    ``|a - b| <= tol * |b| + tol * floor(b)`` with ``floor`` = ``elementwise_floor`` (rms of the tensor; for matrices
+    at least the geometric mean of the entry's row and column rms).  Returns the number of violating entries."""
+    return int((elementwise_ratio(a, b, tol) > 1.0).sum())
 
 
 def assert_rankings_consistent(scores: torch.Tensor, ref: torch.Tensor, labels: torch.Tensor, top_k, tol: float = 1e-4):
