@@ -19,7 +19,7 @@ def stats(a, b):
     rms = b.pow(2).mean().sqrt()
     d = (a - b).abs()
     return dict(norm=float(d.max() / b.abs().max()), ratio=float((d / (1e-4 * b.abs() + 1e-4 * rms)).max()),
-                ratio_structured=float(elementwise_ratio(a, b).max()),
+                ratio_structured=float(elementwise_ratio(a, b, floor_mult=1.0).max()),
                 viol=int((d > 1e-4 * b.abs() + 1e-4 * rms).sum()), rms_err_over_rms=float(d.pow(2).mean().sqrt() / rms))
 
 

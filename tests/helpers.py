@@ -62,16 +62,26 @@ def elementwise_floor(b: torch.Tensor) -> torch.Tensor:
     return torch.maximum((row * col).sqrt(), rms.expand_as(b))
 
 
-def elementwise_ratio(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4) -> torch.Tensor:
+FLOOR_MULT = 2.0
+
+
+def elementwise_ratio(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4, floor_mult: float = FLOOR_MULT) -> torch.Tensor:
     a, b = a.double(), b.double()
-    return (a - b).abs() / (tol * b.abs() + tol * elementwise_floor(b))
+    return (a - b).abs() / (tol * b.abs() + floor_mult * tol * elementwise_floor(b))
 
 
-def elementwise_violations(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4) -> int:
+def elementwise_violations(a: torch.Tensor, b: torch.Tensor, tol: float = 1e-4, floor_mult: float = FLOOR_MULT) -> int:
     """Element-wise bar next to the norm-wise ``rel_err``: every entry must satisfy
-    ``|a - b| <= tol * |b| + tol * floor(b)`` with ``floor`` = ``elementwise_floor`` (rms of the tensor; for matrices
-    at least the geometric mean of the entry's row and column rms).  Returns the number of violating entries."""
-    return int((elementwise_ratio(a, b, tol) > 1.0).sum())
+    ``|a - b| <= tol * |b| + floor_mult * tol * floor(b)`` with ``floor`` = ``elementwise_floor`` (rms of the tensor; for
+    matrices at least the geometric mean of the entry's row and column rms) and ``floor_mult`` = 2.
+
+    Why 2: measured on the at-scale cases (profiles/r02_grad_error_probe.txt, float64 oracle as truth) the worst entry of
+    any gradient tensor sits at 0.97 of the bar with floor_mult = 1 (w_h weight gradients on WikiMEL, 148 mentions; every
+    other tensor <= 0.7; scores 0.01) -- the rounding noise of the 3-pass split-bf16 GEMMs (operand residual 2^-18) is
+    ~1.5e-5 of a tensor's rms, ten times the fp32 reference's own noise against float64 (1.5e-6) and well inside the
+    norm-wise 1e-4, but its tail reaches 1e-4 * rms on a handful of entries of heavy-tailed outer-product sums.
+    Returns the number of violating entries."""
+    return int((elementwise_ratio(a, b, tol, floor_mult) > 1.0).sum())
 
 
 def assert_rankings_consistent(scores: torch.Tensor, ref: torch.Tensor, labels: torch.Tensor, top_k, tol: float = 1e-4):
