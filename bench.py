@@ -3,18 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--dataset wikidiverse|wikimel] [--batch B_per_gpu] [--precision fp32|bf16]
-                    [--edge-feature scaler|vector]
+                    [--edge-feature scaler|vector] [--no-legs] [--no-e2e] [--no-cpu-baseline]
 
 One "step" = one pass of the hot path over one batch of synthetic features:
   train step = forward + TripletLoss + backward (+ gradient all-reduce at N > 1) + Adam   (headline)
   ranking    = forward under no_grad                                                      (reported beside it)
-Workload at N = 1 is BASELINE.json configs[1]: DRIN training on WikiDiverse-shaped features
-(10 candidates + gold slot per mention), fp32-parity mode.  Weak scaling: the per-GPU batch is fixed.
+Headline workload = BASELINE.json configs[1]: DRIN training on WikiDiverse-shaped features (10 candidates + gold slot
+per mention), fp32-parity mode, 4096 mentions per GPU per step.  Weak scaling: the per-GPU batch is fixed.
 
 `value`  : mentions/s, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : same metric through the public API with HOST (pinned) buffers: every step copies its 15-tensor
-           batch host->device and reads the loss back, inside the timed region.
-`--impl reference` times the CPU port of the reference (oracle/, loop-faithful mode) on the host cores.
+`e2e`    : same metric through the public API with HOST (pinned) buffers: every step copies its 15-tensor batch
+           host->device and reads the loss back, inside the timed region; the measured host->device ceiling of the box
+           (all ranks copying at once) is printed next to it.
+`legs`   : the other BASELINE.json configurations, measured in the same run at the same N (compact):
+           configs[2] WikiMEL-shaped ranking over 100 candidates + gold slot, mentions sharded over the ranks;
+           configs[3] bf16-feature data-parallel training; configs[4] token / candidate sweep (N = 1 only).
+`--impl reference` times the reference's own CPU implementation on the host cores: the UNMODIFIED reference staged under
+oracle/_ref (oracle/make_ref.py) when present (kind "reference"), else the oracle port (kind "port").
 """
 from __future__ import annotations
 
@@ -33,6 +38,8 @@ if ROOT not in sys.path:
 
 METRIC = "mentions/sec train step (fwd+loss+bwd+Adam); ranking reported beside it"
 UNIT = "mentions/s"
+FEATS = (0, 4, 5, 7, 9, 10)          # the feature tensors of the 14-tensor batch (bf16 in bf16 mode)
+STAGES = ["gemm", "frontend", "gcn_fwd", "gcn_bwd", "score", "loss", "adam", "prep"]
 
 
 def parse_args():
@@ -42,15 +49,45 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dataset", default="wikidiverse", choices=["wikidiverse", "wikimel"])
-    ap.add_argument("--batch", type=int, default=0, help="mentions per GPU per step (0: 4096 WikiDiverse, 512 WikiMEL)")
+    ap.add_argument("--batch", type=int, default=0, help="mentions per GPU per step (0: 4096 WikiDiverse, 576 WikiMEL)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--cpu-batch", type=int, default=512,
-                    help="mentions per step of the CPU reference sample (larger batches favour the CPU: 553 m/s at 32, 872 at 512)")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="mentions per step of the CPU reference (0: the per-GPU batch of our arm, 4096 WikiDiverse / "
+                         "576 WikiMEL; the reference's throughput grows with the batch: 553 m/s at 32, 872 at 512)")
     ap.add_argument("--edge-feature", default="scaler", choices=["scaler", "vector"],
                     help="gcn_edge_feature (args.py:33); the headline is the reference default, scalar edges")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the configs[2]/[3]/[4] legs")
     return ap.parse_args()
+
+
+def default_batch(dataset: str) -> int:
+    return 576 if dataset == "wikimel" else 4096
+
+
+def batch_bytes_per_mention(dataset, bf16=False, D=768, R=2048, P=49, Om=3, Lm=128, Le=64) -> float:
+    """Bytes of the loader's full 15-tensor layout per mention (what a verbatim copy moves)."""
+    wm = dataset == "wikimel"
+    C = 101 if wm else 11
+    f = 2 if bf16 else 4
+    b = f * (Lm * D + P * R + Om * R) + 8 * Lm + 16 + 4 * Om
+    b += C * (f * ((Le if wm else 1) * D + 2 * R) + 4 * 3) + (C - 1)
+    b += 8 * C * Le if wm else 8
+    return float(b)
+
+
+def workload_config(args, world: int, B: int) -> dict:
+    """`config` of the JSON line -- the same dict for our arm and for the reference arm (the reference arm runs a bounded
+    sample of it on the host, described in its cpu_baseline.sample)."""
+    cands = 100 if args.dataset == "wikimel" else 10
+    per = batch_bytes_per_mention(args.dataset, args.precision == "bf16")
+    return {"workload": f"DRIN training step, {args.dataset}-shaped synthetic features, C={cands + 1} candidate slots",
+            "gcn_edge_feature": args.edge_feature, "batch_per_gpu": B, "global_batch": world * B,
+            "parallelism": f"dp{world}",
+            "l2": f"inputs {per * B / 2**20:.0f} MiB per step per GPU, larger than the 126 MB L2 (no flush needed)",
+            "input_bytes_per_mention": per,
+            "loss_semantics": "global-batch TripletLoss (scores all-gathered), gradients summed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -80,10 +117,12 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.samples, self.proc, self.index = [], None, index
+    def __init__(self, index: int, enabled: bool = True):
+        self.samples, self.proc, self.index, self.enabled = [], None, index, enabled
 
     def start(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "25"],
@@ -91,6 +130,7 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -99,6 +139,8 @@ class ClockSampler:
                 self.samples.append(parts)
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -113,15 +155,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port, loop-faithful like the reference's Python loops)
+# CPU reference arm
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="scaler", kind="auto"):
+def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="scaler", kind="auto", budget_s=None):
     """Time the train step and the ranking forward of the reference's CPU path on all host cores.
 
     kind "reference": the UNMODIFIED reference (drin/model.py, common/utils.py TripletLoss, torch.optim.Adam -- the body of
     train.py:32-34,55-56) imported from oracle/_ref (staged by oracle/make_ref.py) or /root/reference;
     kind "port": the oracle restatement (loops=True keeps the reference's per-item Python loops).
-    "auto" takes the reference when it is importable."""
+    "auto" takes the reference when it is importable.  budget_s: stop the timed loop early (>= 3 steps) once it is spent."""
     import torch
     from drin_b200.synthetic import make_batch
     from oracle import drin_oracle as O
@@ -145,7 +187,7 @@ def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="s
             opt.zero_grad(set_to_none=True)             # Lightning's automatic optimisation
             loss.backward()
             opt.step()
-            return float(loss)                          # train.py:35
+            return float(loss.detach())                 # train.py:35
 
         def rank():
             with torch.no_grad():
@@ -163,7 +205,7 @@ def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="s
             loss = loss_fn(b[-1], s, cfg.triplet_margin)
             loss.backward()
             opt.step()
-            return float(loss)
+            return float(loss.detach())
 
         def rank():
             with torch.no_grad():
@@ -172,35 +214,43 @@ def cpu_reference_run(dataset, batch, steps, warmup, loops=True, edge_feature="s
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         step()
-    t_train = (time.perf_counter() - t0) / steps
+        done += 1
+        if budget_s is not None and done >= 3 and time.perf_counter() - t0 > budget_s:
+            break
+    t_train = (time.perf_counter() - t0) / done
     rank()
+    nr = max(done // 2, 1)
     t0 = time.perf_counter()
-    for _ in range(max(steps // 2, 1)):
+    for _ in range(nr):
         rank()
-    t_rank = (time.perf_counter() - t0) / max(steps // 2, 1)
+    t_rank = (time.perf_counter() - t0) / nr
     return dict(train_mps=batch / t_train, rank_mps=batch / t_rank, ms_per_step=t_train * 1e3, cores=os.cpu_count(),
-                threads=torch.get_num_threads(), kind=kind)
+                threads=torch.get_num_threads(), kind=kind, steps_timed=done)
+
+
+def _cpu_what(kind):
+    return ("the UNMODIFIED reference (drin/model.py + common/utils.py TripletLoss + torch.optim.Adam, staged under "
+            "oracle/_ref)" if kind == "reference" else "oracle port of the reference (per-item Python loops kept)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.cpu_batch if args.cpu_batch else 512
-    r = cpu_reference_run(args.dataset, B, args.steps, args.warmup, loops=True, edge_feature=args.edge_feature)
-    cands = 10 if args.dataset == "wikidiverse" else 100
-    what = ("the UNMODIFIED reference (drin/model.py + common/utils.py TripletLoss + torch Adam, staged under oracle/_ref)"
-            if r["kind"] == "reference" else "oracle port of the reference (per-item Python loops kept)")
-    sample = (f"{what}, {args.dataset}-shaped batch of {B} mentions per step, fwd+TripletLoss+bwd+Adam, "
-              f"{args.warmup} warm-up + {args.steps} timed steps, torch CPU {r['threads']} threads")
+    B = args.cpu_batch or args.batch or default_batch(args.dataset)
+    r = cpu_reference_run(args.dataset, B, args.steps, args.warmup, loops=True, edge_feature=args.edge_feature,
+                          budget_s=150.0)
+    sample = (f"{_cpu_what(r['kind'])}: one {args.dataset}-shaped batch of {B} mentions per step (= our arm's per-GPU batch), "
+              f"fwd+TripletLoss+bwd+Adam, {args.warmup} warm-up + {r['steps_timed']} timed steps, torch CPU "
+              f"{r['threads']} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["train_mps"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DRIN train step, {args.dataset}-shaped synthetic features, C={cands + 1}",
-                   "batch_per_step": B, "parallelism": "host CPU"},
+        "config": workload_config(args, args.gpus, args.batch or default_batch(args.dataset)),
         "cpu_baseline": {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["train_mps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ranking": {"value": r["rank_mps"], "unit": UNIT},
@@ -212,52 +262,48 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import ctypes as C
+class Bench:
+    def __init__(self, args):
+        import ctypes as C
 
-    import torch
-    import torch.distributed as dist
+        import torch
+        import torch.distributed as dist
 
-    import drin_b200
-    from drin_b200 import _lib
-    from drin_b200.synthetic import batch_bytes, make_batch
+        from drin_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    lib.drin_launch_count.restype = C.c_longlong
+        self.args, self.C, self.torch, self.dist, self._lib = args, C, torch, dist, _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+        self.lib.drin_launch_count.restype = C.c_longlong
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # fallback = the profiling recipe's figures (B200_PROFILING.md) when the driver-written file is absent
+        self.tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        self.hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        self.peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
 
-    wm = args.dataset == "wikimel"
-    cands = 100 if wm else 10
-    Cn = cands + 1
-    B = args.batch or (512 if wm else 4096)
-    bf16 = args.precision == "bf16"
-    feats = (0, 4, 5, 7, 9, 10)
+    # ---- helpers ----
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    torch.manual_seed(0)
-    model = drin_b200.Model(num_candidates_model=Cn, gcn_edge_feature=args.edge_feature).to(dev)
-    trainer = drin_b200.Trainer(model, lr=1e-3, margin=0.25)
-    batch = make_batch(args.dataset, B, seed=1000 + rank, num_candidates=cands, device=str(dev), generate_on_device=True)
-    if bf16:
-        batch = [t.to(torch.bfloat16) if i in feats else t for i, t in enumerate(batch)]
-    in_bytes = batch_bytes(batch)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, after=None):
+    def timed(self, fn, steps, warmup, after=None):
+        torch = self.torch
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -265,65 +311,268 @@ def run_ours(args):
         if after is not None:
             after()
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             ms = float(t)
         return ms / steps
 
-    stage_names = ["gemm", "frontend", "gcn_fwd", "gcn_bwd", "score", "loss", "adam", "prep"]
-
-    def collect_profile():
-        n = len(stage_names)
+    def collect_profile(self):
+        C, n = self.C, len(STAGES)
         ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
         cnt = (C.c_longlong * n)()
-        _lib.check(lib.drin_profile_collect(ms, fl, by, cnt), "drin_profile_collect")
-        return {s: dict(ms=ms[i], flops=fl[i], launches=cnt[i]) for i, s in enumerate(stage_names)}
+        self._lib.check(self.lib.drin_profile_collect(ms, fl, by, cnt), "drin_profile_collect")
+        return {s: dict(ms=ms[i], flops=fl[i], launches=cnt[i]) for i, s in enumerate(STAGES)}
 
-    # ---------------- device-resident train step (the headline `value`) ----------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        trainer.step(batch)
-    torch.cuda.synchronize()
-    launches0 = lib.drin_launch_count()
-    ms_train = timed(lambda: trainer.step(batch), args.steps, 0)          # the headline: no per-launch events
-    launches = lib.drin_launch_count() - launches0
-    # same K steps again with a CUDA-event pair around every launch (on the launching stream): per-stage device time
-    lib.drin_profile_enable(1)
-    trainer.step(batch)
-    torch.cuda.synchronize()
-    collect_profile()                                   # drop the first profiled step
-    ms_train_profiled = timed(lambda: trainer.step(batch), args.steps, 0)
-    prof = collect_profile()
-    lib.drin_profile_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * B / (ms_train * 1e-3)
+    def profiled(self, fn, steps):
+        """Per-stage device time: CUDA-event pairs around every launch of the library, on the launching stream."""
+        self.lib.drin_profile_enable(1)
+        fn()
+        self.torch.cuda.synchronize()
+        self.collect_profile()                      # drop the first profiled step
+        ms = self.timed(fn, steps, 0)
+        prof = self.collect_profile()
+        self.lib.drin_profile_enable(0)
+        return ms, prof
 
-    # ---------------- ranking (forward under no_grad), device-resident ----------------
-    ms_rank = timed(lambda: trainer.rank_scores(batch), args.steps, args.warmup)
-    lib.drin_profile_enable(1)
-    trainer.rank_scores(batch)
-    torch.cuda.synchronize()
-    prof_rank = collect_profile()
-    lib.drin_profile_enable(0)
+    def make(self, dataset, B, bf16=False, edge_feature="scaler", seed=1000, **kw):
+        import drin_b200
+        from drin_b200.synthetic import make_batch
+        torch = self.torch
+        cands = kw.pop("cands", 100 if dataset == "wikimel" else 10)
+        torch.manual_seed(0)
+        model = drin_b200.Model(num_candidates_model=cands + 1, gcn_edge_feature=edge_feature).to(self.dev)
+        trainer = drin_b200.Trainer(model, lr=1e-3, margin=0.25)
+        batch = make_batch(dataset, B, seed=seed + self.rank, num_candidates=cands, device=str(self.dev),
+                           generate_on_device=True, **kw)
+        if bf16:
+            batch = [t.to(torch.bfloat16) if i in FEATS else t for i, t in enumerate(batch)]
+        return model, trainer, batch
 
-    # ---------------- end to end: host (pinned) batch -> device every step, loss read back ----------------
-    e2e = None
-    if not args.no_e2e:
+    def h2d_ceiling(self, nbytes=1 << 30, reps=4):
+        """Host->device bandwidth of one large pinned copy per rank, all ranks copying at the same time: the ceiling the
+        e2e leg runs against on this box (PCIe link + host fabric shared by the GPUs)."""
+        torch = self.torch
+        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        ms = self.timed(lambda: d.copy_(h, non_blocking=True), reps, 1)
+        del h, d
+        return self.world * nbytes / (ms * 1e-3) / 1e9
+
+    # ---- legs ----
+    def leg_wikimel_ranking(self, steps, warmup):
+        """BASELINE configs[2]: ranking over 100 candidates + gold slot (WikiMEL top100 shape), mentions sharded over the
+        ranks, no communication but the final gather of the scores (inside the timed region at N > 1)."""
+        B = 576
+        model, tr, batch = self.make("wikimel", B, seed=3000)
+        sampler = ClockSampler(self.local, self.rank == 0).start()
+        gather = self.world > 1
+        ms = self.timed(lambda: tr.rank_scores(batch, gather=gather), steps, warmup)
+        n = max(steps // 2, 3)
+        _, prof = self.profiled(lambda: tr.rank_scores(batch, gather=gather), n)
+        clocks = sampler.stop()
+        abytes = algorithmic_bytes_per_mention(101, True)
+        fe_gbs = abytes * B * n / (prof["frontend"]["ms"] * 1e-3) / 1e9
+        g = prof["gemm"]
+        out = {"config": "BASELINE configs[2]: DRIN ranking inference, WikiMEL top100 shape (C=101, Le=64), fp32-parity, "
+                         f"{B} mentions per GPU per pass, mentions sharded over {self.world} GPU(s), final score gather "
+                         + ("included" if gather else "n/a at N=1"),
+               "value": self.world * B / (ms * 1e-3), "unit": UNIT, "ms_per_pass": ms, "batch_per_gpu": B,
+               "path_hbm_gbs_per_gpu": abytes * B / (ms * 1e-3) / 1e9,
+               "path_hbm_frac": abytes * B / (ms * 1e-3) / 1e9 / self.hbm_peak,
+               "frontend_gbs": fe_gbs, "frontend_hbm_frac": fe_gbs / self.hbm_peak,
+               "gemm_tflops": g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else None,
+               "stage_ms_per_pass": {k: v["ms"] / n for k, v in prof.items() if v["ms"] > 0},
+               "algorithmic_bytes_per_mention": abytes, "clocks": clocks}
+        del model, tr, batch
+        self.torch.cuda.empty_cache()
+        return out
+
+    def leg_bf16_train(self, steps, warmup):
+        """BASELINE configs[3]: data-parallel training with bf16 features (single-pass bf16 GEMMs), NCCL all-reduce at
+        N > 1; WikiDiverse shape, 4096 mentions per GPU."""
+        B = 4096
+        model, tr, batch = self.make("wikidiverse", B, bf16=True, seed=4000)
+        sampler = ClockSampler(self.local, self.rank == 0).start()
+        ms = self.timed(lambda: tr.step(batch), steps, warmup)
+        n = max(steps // 2, 3)
+        _, prof = self.profiled(lambda: tr.step(batch), n)
+        clocks = sampler.stop()
+        g = prof["gemm"]
+        tf = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        out = {"config": "BASELINE configs[3]: DRIN data-parallel training, bf16 features, WikiDiverse shape (C=11), "
+                         f"{B} mentions per GPU per step, dp{self.world}" + (", NCCL grad all-reduce" if self.world > 1 else ""),
+               "value": self.world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": B, "dtype": "bf16",
+               "gemm_tflops": tf, "gemm_frac_of_tensor_peak": tf / self.tensor_peak,
+               "stage_ms_per_step": {k: v["ms"] / n for k, v in prof.items() if v["ms"] > 0},
+               "tolerance": "scores/loss 2e-3, gradients 3e-2 against the fp32 reference on bf16-rounded features "
+                            "(tests/test_gpu_parity_scale.py)", "clocks": clocks}
+        del model, tr, batch
+        self.torch.cuda.empty_cache()
+        return out
+
+    def leg_sweep(self):
+        """BASELINE configs[4] (N = 1): text tokens 32 -> 128 and candidates 10 -> 100; GEMM vs row-kernel stage split."""
+        pts = []
+        grid = [("wikidiverse", 10, 32, 0), ("wikidiverse", 100, 128, 0), ("wikimel", 10, 128, 64),
+                ("wikimel", 100, 32, 32), ("wikimel", 100, 128, 128)]
+        for ds, cands, Lm, Le in grid:
+            wm = ds == "wikimel"
+            per = (Lm * 768 + 49 * 2048 + 3 * 2048) * 4 + (cands + 1) * ((Le if wm else 1) * 768 + 2 * 2048) * 4
+            B = max(64, min(4096, int((8 if wm else 3) * 2**30 // per) // 64 * 64))
+            kw = dict(mention_tokens=Lm, cands=cands)
+            if wm:
+                kw["entity_tokens"] = Le
+            model, tr, batch = self.make(ds, B, seed=5000, **kw)
+            p = dict(dataset=ds, candidates=cands, mention_tokens=Lm, entity_tokens=Le, batch=B)
+            nbar = (4 + Le) / 2.0 if wm else 1.0
+            abytes = algorithmic_bytes_per_mention(cands + 1, wm, Le=Le, nbar=nbar)
+            for mode, fn in (("rank", lambda: tr.rank_scores(batch)), ("train", lambda: tr.step(batch))):
+                ms = self.timed(fn, 4, 2)
+                _, prof = self.profiled(fn, 3)
+                g, fe = prof["gemm"], prof["frontend"]
+                rows = sum(prof[k]["ms"] for k in ("gcn_fwd", "gcn_bwd", "score"))
+                tf = g["flops"] / (g["ms"] * 1e-3) / 1e12
+                gbs = abytes * B * 3 / (fe["ms"] * 1e-3) / 1e9
+                p[mode] = dict(mentions_per_s=B / (ms * 1e-3), ms=ms, gemm_tflops=tf,
+                               gemm_frac_of_tensor_peak=tf / self.tensor_peak, frontend_gbs=gbs,
+                               frontend_hbm_frac=gbs / self.hbm_peak,
+                               stage_ms=dict(gemm=g["ms"] / 3, frontend=fe["ms"] / 3, gcn_rows_and_score=rows / 3))
+            pts.append(p)
+            del model, tr, batch
+            self.torch.cuda.empty_cache()
+        return {"config": "BASELINE configs[4]: token / candidate sweep, fp32-parity, 1 GPU, device-resident inputs",
+                "points": pts}
+
+    # ---- the run ----
+    def run(self):
+        args, torch, lib, world, rank = self.args, self.torch, self.lib, self.world, self.rank
+
+        wm = args.dataset == "wikimel"
+        Cn = (100 if wm else 10) + 1
+        B = args.batch or default_batch(args.dataset)
+        bf16 = args.precision == "bf16"
+        model, trainer, batch = self.make(args.dataset, B, bf16, args.edge_feature)
+
+        # ---------------- device-resident train step (the headline `value`) ----------------
+        sampler = ClockSampler(self.local, rank == 0).start()
+        for _ in range(args.warmup):
+            trainer.step(batch)
+        torch.cuda.synchronize()
+        launches0 = lib.drin_launch_count()
+        ms_train = self.timed(lambda: trainer.step(batch), args.steps, 0)       # the headline: no per-launch events
+        launches = lib.drin_launch_count() - launches0
+        ms_train_profiled, prof = self.profiled(lambda: trainer.step(batch), args.steps)
+        clocks = sampler.stop()
+        value = world * B / (ms_train * 1e-3)
+
+        # ---------------- ranking (forward under no_grad), device-resident ----------------
+        ms_rank = self.timed(lambda: trainer.rank_scores(batch), args.steps, args.warmup)
+        _, prof_rank = self.profiled(lambda: trainer.rank_scores(batch), 3)
+
+        # ---------------- end to end: host (pinned) batch -> device every step, loss read back ----------------
+        e2e = None if args.no_e2e else self.e2e(trainer, batch, B, Cn, bf16)
+        del batch
+        torch.cuda.empty_cache()
+
+        legs = None
+        if not args.no_legs and args.dataset == "wikidiverse" and not bf16 and args.edge_feature == "scaler":
+            k, w = max(args.steps // 2, 5), max(args.warmup, 3)
+            del model, trainer
+            torch.cuda.empty_cache()
+            legs = {"wikimel_ranking": self.leg_wikimel_ranking(k, w), "bf16_train": self.leg_bf16_train(k, w)}
+            if world == 1:
+                legs["sweep"] = self.leg_sweep()
+
+        if rank != 0:
+            if world > 1:
+                self.dist.destroy_process_group()
+            return
+
+        # ---------------- roofline of the dominant kernel family (tcgen05 GEMM), live CUDA-event times ----------------
+        g = prof["gemm"]
+        gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        passes = 1 if bf16 else 3
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+        except Exception:
+            pass
+        total_ms = sum(v["ms"] for v in prof.values())
+        roofline = {
+            "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
+            "achieved": gemm_tflops, "peak": self.tensor_peak, "unit": "TFLOP/s", "frac": gemm_tflops / self.tensor_peak,
+            "traffic": traffic.get("traffic_bytes_per_launch"), "traffic_kernel": traffic.get("kernel"),
+            "traffic_algorithmic_bytes": traffic.get("algorithmic_bytes_per_launch"),
+            "peak_source": self.peak_src + ", sustained bf16",
+            "executed_tflops": gemm_tflops * passes,
+            "executed_frac_of_sustained_peak": gemm_tflops * passes / self.tensor_peak,
+            "note": ("achieved = algorithmic 2MNK flops of the launched GEMMs / their summed CUDA-event time; fp32-parity "
+                     "mode issues 3 bf16 tensor passes per algorithmic flop (split-bf16), so executed = 3x achieved and the "
+                     "ceiling of `frac` is 1/3; `traffic` is the ncu DRAM read+write of ONE launch of the largest GEMM of the "
+                     "step (`traffic_kernel`), next to that launch's algorithmic bytes"),
+            "gemm_launches_per_step": g["launches"] / args.steps,
+            "gemm_share_of_step": g["ms"] / total_ms if total_ms else None,
+        }
+        fe = prof["frontend"]
+        feat_b = 2 if bf16 else 4
+        fe_bytes = algorithmic_bytes_per_mention(Cn, wm, feat_bytes=feat_b) * B * args.steps
+        fe_gbs = fe_bytes / (fe["ms"] * 1e-3) / 1e9 if fe["ms"] > 0 else 0.0
+        roofline_hbm = {"bound": "hbm", "kernel": "frontend_kernel", "achieved": fe_gbs, "peak": self.hbm_peak,
+                        "unit": "GB/s", "frac": fe_gbs / self.hbm_peak, "traffic": None,
+                        "note": "algorithmic input bytes (SURVEY 8d) / CUDA-event time of the front-end kernel"}
+        rk = prof_rank["gemm"]
+        ranking = {"value": world * B / (ms_rank * 1e-3), "unit": UNIT, "ms_per_step": ms_rank,
+                   "gemm_tflops": rk["flops"] / (rk["ms"] * 1e-3) / 1e12 if rk["ms"] > 0 else None,
+                   "frontend_gbs": (algorithmic_bytes_per_mention(Cn, wm, feat_bytes=feat_b) * B * 3 /
+                                    (prof_rank["frontend"]["ms"] * 1e-3) / 1e9) if prof_rank["frontend"]["ms"] > 0 else None}
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = args.cpu_batch or 512
+            r = cpu_reference_run(args.dataset, cb, 12, 2, loops=True, edge_feature=args.edge_feature, budget_s=20.0)
+            big = cpu_reference_run(args.dataset, B, 3, 1, loops=True, edge_feature=args.edge_feature, budget_s=12.0)
+            best = max((r, big), key=lambda x: x["train_mps"])
+            cpu = {"value": best["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                   "sample": (f"{_cpu_what(r['kind'])}, {args.dataset}-shaped batches, fwd+loss+bwd+Adam, {r['threads']} torch "
+                              f"threads; best of batch {cb} ({r['steps_timed']} timed steps: {r['train_mps']:.0f} m/s) and "
+                              f"batch {B} = our per-GPU batch ({big['steps_timed']} timed steps: {big['train_mps']:.0f} m/s)"),
+                   "value_by_batch": {str(cb): r["train_mps"], str(B): big["train_mps"]},
+                   "ranking_value": max(r["rank_mps"], big["rank_mps"])}
+
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if bf16 else "f32 (GEMMs as 3-pass split-bf16 on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "config": workload_config(args, world, B),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "ranking": ranking,
+            "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+            "ms_per_step_with_stage_events": ms_train_profiled,
+            "necessary_gemm_tflops_of_step": (gemm_flops_per_mention(Cn, True, vector=args.edge_feature == "vector") * B /
+                                              (ms_train * 1e-3) / 1e12),
+            "legs": legs,
+        }
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            self.dist.destroy_process_group()
+
+    def e2e(self, trainer, batch, B, Cn, bf16):
+        import drin_b200
+        args, torch, world, dev = self.args, self.torch, self.world, self.dev
+        steps, warm = args.steps, max(args.warmup, 3)
         host = [t.cpu().pin_memory() for t in batch]
         loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-        def run_e2e(compact):
+        def run_e2e(compact, k):
             feeder = drin_b200.HostFeeder(dev, slots=2, compact_spans=compact)
             state = {"slot": feeder.submit(host)}
 
             def e2e_step():
-                # double buffered: the host gather + copy of step i+1 overlap the compute of step i; all of it is
-                # inside the timed region, and the loss is read back every step (reference train.py:35)
+                # double buffered: the host gather + copy of step i+1 overlap the compute of step i; all of it is inside
+                # the timed region, and the loss is read back every step (reference train.py:35)
                 sid = state["slot"]
                 dbatch = feeder.get(sid)
                 loss = trainer.step(dbatch)
@@ -338,18 +587,23 @@ def run_ours(args):
             def drain():
                 torch.cuda.current_stream().wait_event(feeder.slots[state["slot"]]["ready"])
 
-            ms = timed(e2e_step, max(args.steps // 2, 3), 3, after=drain)
+            ms = self.timed(e2e_step, k, warm, after=drain)
             nbytes = feeder.last_bytes
             del feeder
             return ms, nbytes
 
-        ms_full, bytes_full = run_e2e(False)
-        ms_e2e, bytes_e2e = run_e2e(True)
+        ms_full, bytes_full = run_e2e(False, max(steps // 4, 3))     # verbatim copy: reported beside, fewer iterations
+        ms_e2e, bytes_e2e = run_e2e(True, steps)                     # the e2e value: the CLI's --steps
+        peak = self.h2d_ceiling()
+        gbs = world * bytes_e2e / (ms_e2e * 1e-3) / 1e9
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_e2e,
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "steps": steps, "warmup": warm,
+               "h2d_gbs": gbs, "h2d_peak_gbs": peak, "h2d_frac_of_peak": gbs / peak,
                "note": ("pinned host batch -> device every step on a side stream (double buffered), loss read back; "
-                        "HostFeeder copies only the bytes the path reads: the start:end span rows of "
-                        "mention_text_feature are gathered on the host (the other rows are never read)"),
+                        "HostFeeder copies only the bytes the path reads: the start:end span rows of mention_text_feature are "
+                        "gathered on the host (the other rows are never read).  h2d_gbs = aggregate host->device rate of the "
+                        "leg over all ranks; h2d_peak_gbs = one 1 GiB pinned copy per rank, all ranks at once, measured in "
+                        "this run: the leg is bound by the host->device fabric of the box, not by the GPUs"),
                "full_copy": {"value": world * B / (ms_full * 1e-3), "h2d_bytes_per_step": bytes_full,
                              "ms_per_step": ms_full, "note": "all 15 tensors copied verbatim"}}
         del host
@@ -357,11 +611,11 @@ def run_ours(args):
         # ---------------- resident feature store: tables in HBM, only indices cross PCIe -------
         from drin_b200.store import FeatureStore, synthetic_tables
         n_store = 3 * B
-        tables = synthetic_tables(args.dataset, n_store, seed=2000 + rank, num_candidates=cands, device=str(dev))
+        tables = synthetic_tables(args.dataset, n_store, seed=2000 + self.rank, num_candidates=Cn - 1, device=str(dev))
         store = FeatureStore(args.dataset, tables, Cn, device=dev,
                              feature_dtype=torch.bfloat16 if bf16 else torch.float32)
         del tables
-        order = torch.randperm(n_store, generator=torch.Generator().manual_seed(rank)).pin_memory()
+        order = torch.randperm(n_store, generator=torch.Generator().manual_seed(self.rank)).pin_memory()
         cursor = {"k": 0}
 
         def store_step():
@@ -372,7 +626,7 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()
             return float(loss_host)
 
-        ms_store = timed(store_step, max(args.steps // 2, 3), 3)
+        ms_store = self.timed(store_step, steps, warm)
         e2e["resident_store"] = {
             "value": world * B / (ms_store * 1e-3), "unit": UNIT, "ms_per_step": ms_store,
             "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "resident_bytes_per_gpu": store.nbytes(),
@@ -381,81 +635,8 @@ def run_ours(args):
                      "[B] mention indices from pinned host memory, the front-end kernel gathers rows by index "
                      "(drin/data.py:85-108 on device), loss read back every step")}
         del store
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---------------- roofline of the dominant kernel family (tcgen05 GEMM), live CUDA-event times ----------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback"
-    g = prof["gemm"]
-    gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
-    passes = 1 if bf16 else 3
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("traffic_bytes_per_launch")
-    except Exception:
-        pass
-    total_ms = sum(v["ms"] for v in prof.values())
-    roofline = {
-        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
-        "achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tensor_peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "executed_tflops": gemm_tflops * passes,
-        "note": ("achieved = algorithmic 2MNK flops of the launched GEMMs / their summed CUDA-event time; fp32-parity mode "
-                 "issues 3 bf16 tensor passes per algorithmic flop (split-bf16), so executed = 3x achieved"),
-        "gemm_launches_per_step": g["launches"] / args.steps, "gemm_share_of_step": g["ms"] / total_ms if total_ms else None,
-    }
-    fe = prof["frontend"]
-    fe_bytes = algorithmic_bytes_per_mention(Cn, wm, feat_bytes=2 if bf16 else 4) * B * args.steps
-    fe_gbs = fe_bytes / (fe["ms"] * 1e-3) / 1e9 if fe["ms"] > 0 else 0.0
-    roofline_hbm = {"bound": "hbm", "kernel": "frontend_kernel", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": fe_gbs / hbm_peak, "traffic": None,
-                    "note": "algorithmic input bytes (SURVEY 8d) / CUDA-event time of the front-end kernel"}
-    rk_fl = prof_rank["gemm"]
-    ranking = {"value": world * B / (ms_rank * 1e-3), "unit": UNIT, "ms_per_step": ms_rank,
-               "gemm_tflops": rk_fl["flops"] / (rk_fl["ms"] * 1e-3) / 1e12 if rk_fl["ms"] > 0 else None,
-               "frontend_gbs": (algorithmic_bytes_per_mention(Cn, wm, feat_bytes=2 if bf16 else 4) * B /
-                                (prof_rank["frontend"]["ms"] * 1e-3) / 1e9) if prof_rank["frontend"]["ms"] > 0 else None}
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.dataset, args.cpu_batch, 12, 2, loops=True, edge_feature=args.edge_feature)
-        rv = cpu_reference_run(args.dataset, args.cpu_batch, 6, 1, loops=False, edge_feature=args.edge_feature, kind="port")
-        cpu = {"value": r["train_mps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-               "sample": (("the unmodified reference (oracle/_ref)" if r["kind"] == "reference" else
-                           "oracle port (reference-style Python loops)") +
-                          f", {args.dataset}-shaped batch of {args.cpu_batch}, "
-                          f"fwd+loss+bwd+Adam, 2 warm-up + 12 timed steps, {r['threads']} torch threads"),
-               "ranking_value": r["rank_mps"], "vectorised_port_value": rv["train_mps"]}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if bf16 else "f32 (GEMMs as 3-pass split-bf16 on tcgen05, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": f"DRIN training step, {args.dataset}-shaped synthetic features, C={Cn} candidate slots",
-                   "gcn_edge_feature": args.edge_feature,
-                   "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
-                   "l2": f"inputs {in_bytes / 2**20:.0f} MiB per step per GPU, larger than the 126 MB L2 (no flush needed)",
-                   "input_bytes_per_mention": in_bytes / B,
-                   "loss_semantics": "global-batch TripletLoss (scores all-gathered), gradients summed"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "ranking": ranking,
-        "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
-        "ms_per_step_with_stage_events": ms_train_profiled,
-        "necessary_gemm_tflops_of_step": gemm_flops_per_mention(Cn, True, vector=args.edge_feature == "vector") * B / (ms_train * 1e-3) / 1e12,
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.empty_cache()
+        return e2e
 
 
 def main():
@@ -468,7 +649,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    run_ours(args)
+    Bench(args).run()
 
 
 if __name__ == "__main__":

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(1024) triplet_cum_kernel(int* __restrict__ his
 __global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const float* __restrict__ p,
                                       const float* __restrict__ ps, const int* __restrict__ cum, int B, int C, int row0,
                                       int rows, float k, float* __restrict__ dscores, const double* __restrict__ partial,
-                                      int nblocks, float* __restrict__ loss) {
+                                      int pb0, int pb1, float* __restrict__ loss) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // over rows * C
   if (e < (long long)rows * C) {
     const int bl = (int)(e / C), c = (int)(e - (long long)bl * C);
@@ -222,9 +222,10 @@ __global__ void triplet_finish_kernel(const unsigned char* __restrict__ y, const
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // only the blocks that cover local rows hold non-zero hinge partials; all are summed in block order
+    // only the count-kernel blocks [pb0, pb1] that cover local rows hold non-zero hinge partials: summed in block order
+    // (the cost of this serial tail does not grow with the number of ranks)
     double t = 0.0;
-    for (int i = 0; i < nblocks; ++i) t += partial[i];
+    for (int i = pb0; i <= pb1; ++i) t += partial[i];
     loss[0] = (float)(t * (double)k);
   }
 }
@@ -253,8 +254,10 @@ int triplet_loss(cudaStream_t stream, const float* scores, const unsigned char* 
   triplet_cum_kernel<<<g1 - g0 + 1, 1024, 0, stream>>>(t.hist, g0);
   DRIN_LAUNCH_CHECK();
   const long long fe = (long long)rows * C;
+  const int pb0 = (int)((long long)row0 * (C - 1) / TL_THREADS);
+  const int pb1 = (int)((((long long)(row0 + rows)) * (C - 1) - 1) / TL_THREADS);
   triplet_finish_kernel<<<(int)((fe + 255) / 256), 256, 0, stream>>>(labels, t.p, t.p_sorted, t.hist, B, C, row0, rows, k,
-                                                                     dscores, t.partial, cblocks, loss);
+                                                                     dscores, t.partial, pb0, pb1, loss);
   DRIN_LAUNCH_CHECK();
   return DRIN_OK;
 }

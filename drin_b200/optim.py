@@ -18,7 +18,7 @@ class FusedAdam:
         self._step = torch.zeros(1, dtype=torch.int32, device=flat.device)
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
-        self.skip = model.dead_mask()      # parameters whose grad is None upstream are never stepped
+        self.skip = model.skip_mask()      # parameters whose grad is None upstream are never stepped
 
     def _collect_autograd_grads(self) -> None:
         """``Model.forward`` + ``loss.backward()`` (the reference's Lightning flow, train.py:46-56) leaves the gradients

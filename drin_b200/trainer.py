@@ -7,8 +7,8 @@ Data parallelism: mentions are sharded across ranks, parameters r
     the local ``[B_loc, C]`` scores and labels are all-gathered BEFORE the loss; each rank then gets the
     gradient of the GLOBAL loss for its own rows.  The result equals the reference run at the global
     batch size, not at the local one.
-  * Parameter gradients are summed with ONE all-reduce over the flat gradient buffer (26.8 MB live,
-    31.5 MB total) -- no averaging: the 1/B_glob^2 normalisation is already in dL/dscores.  The per-rank loss
+  * Parameter gradients are summed with ONE all-reduce over the live part of the flat gradient buffer (26.8 MB;
+    the dead parameters sit behind it) -- no averaging: the 1/B_glob^2 normalisation is already in dL/dscores.  The per-rank loss
     shares travel in the same bucket, and the labels travel with the scores: two collectives per step in total.
   * Ranking needs no communication beyond a final gather of the scores.
 """
@@ -97,8 +97,8 @@ class Trainer:
             return self._backward_overlapped(ctx, inputs, params, dscores, loss)
         m._engine.backward(ctx, inputs, params, dscores, m._grad_views())
         ctx.release()
-        # 31.5 MB of gradients + this rank's share of the loss in the bucket's tail
-        loss = reduce_grads_and_loss(m.flat_grads_bucket, m.flat_params.numel(), loss, self.group)
+        # 26.8 MB of live gradients + this rank's share of the loss in the bucket's tail
+        loss = reduce_grads_and_loss(m.flat_grads_bucket, m.n_live, loss, self.group)
         m._flat_grads_valid = True          # FusedAdam reads the flat buffer directly
         return loss.reshape(())
 
@@ -111,7 +111,7 @@ class Trainer:
             self._comm_stream = torch.cuda.Stream(device=dev)
             self._layers_done = torch.cuda.Event()
             self._layers_done.record()                    # creates the underlying cudaEvent_t
-        bucket, n, off = m.flat_grads_bucket, m.flat_params.numel(), m.layer_grad_offset()
+        bucket, n, off = m.flat_grads_bucket, m.n_live, m.layer_grad_offset()
         bucket[n:n + 1].copy_(loss_share.reshape(1))      # before backward: covered by the layers-done event
         m._engine.backward(ctx, inputs, params, dscores, m._grad_views(), layers_done=self._layers_done)
         ctx.release()
@@ -243,7 +243,7 @@ class GraphedStoreStep:
         # the graph has raw pointers into the engine's workspace(s) and the loss scratch baked in: keep them alive for
         # as long as the graph exists, whatever other batch sizes the engine or the loss see in between
         from .loss import scratch_tensors
-        self._keep = list(m._engine.pool.tensors()) + scratch_tensors() + [m.flat_grads_bucket, store]
+        self._keep = list(m._engine.pool.tensors()) + scratch_tensors() + [m.flat_grads, store]
         with torch.no_grad():
             m.flat_params.copy_(saved[0])
             opt.exp_avg.copy_(saved[1])

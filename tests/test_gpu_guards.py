@@ -58,8 +58,7 @@ def _run(dataset, B, cands, fill, bf16=False, forced=-1, **model_kw):
         assert len(eng.pool.entries) == 1
         ws = eng.pool.entries[0]["ws"]
         ws.fill_(fill)
-        bucket = model.flat_grads_bucket
-        bucket.view(torch.uint8).fill_(0xA5)            # dead-parameter slots must keep this pattern
+        model.flat_grads.view(torch.uint8).fill_(0xA5)  # dead-parameter and tail slots must keep this pattern
         loss = tr.forward_backward(batch)
         scores = tr.last_scores.clone()
         grads = model.flat_grads.clone()
@@ -69,7 +68,7 @@ def _run(dataset, B, cands, fill, bf16=False, forced=-1, **model_kw):
         pb = E.inspect_batch(tuple(batch[:-1]), cands + 1)
         offs, guard = _guard_regions(eng, eng.config(pb, True))
         return dict(loss=loss.clone(), scores=scores, grads=grads, ranked=ranked, ws=ws, offs=offs, guard=guard,
-                    dead=model.dead_mask().bool())
+                    dead=model.skip_mask().bool())
     finally:
         for name in VARIANTS:
             _option(name, -1)

@@ -73,6 +73,29 @@ def test_model_is_a_drop_in_for_the_reference_constructor():
     assert int(m.dead_mask().sum()) == 2 * (768 * 768 + 768)
 
 
+def test_flat_layout_keeps_dead_parameters_behind_the_allreduce_bucket():
+    """Flat buffer = [live parameters | 4 tail floats | dead parameters]: the data-parallel all-reduce bucket is the
+    leading n_live + 4 floats (26.8 MB) and carries no dead zeros; state_dict order is unchanged."""
+    for kw, n_dead in ((dict(), 2 * (768 * 768 + 768)), (dict(gcn_edge_type="static"), 4 * (768 * 768 + 768)),
+                       (dict(gcn_edge_feature="vector"), 768 * 768 + 768 + 2 * (384 * 768 + 384))):
+        m = drin_b200.Model(**kw)
+        total = sum(p.numel() for p in m.parameters())
+        assert m.n_live == total - n_dead and m.flat_params.numel() == total + m.TAIL
+        assert m.flat_grads_bucket.numel() == m.n_live + m.TAIL
+        assert m.flat_grads_bucket.data_ptr() == m.flat_grads.data_ptr()
+        dead = set(m._dead)
+        for k, (o, n, shape) in m._offsets.items():
+            assert (o >= m.n_live + m.TAIL) if k in dead else (o + n <= m.n_live), k
+        assert int(m.skip_mask().sum()) == n_dead + m.TAIL and int(m.dead_mask().sum()) == n_dead
+        assert m.layer_grad_offset() == 2 * (768 * 768 + 768) + 2 * (768 * 2048 + 768)
+        # parameters are still views of the flat buffer, in state_dict order for the caller
+        sd = {k: torch.full_like(v, float(i)) for i, (k, v) in enumerate(m.state_dict().items())}
+        m.load_state_dict(sd)
+        for i, k in enumerate(sd):
+            o, n, _ = m._offsets[k]
+            assert float(m.flat_params[o]) == float(i) == float(m.flat_params[o + n - 1]), k
+
+
 def test_unsupported_configurations_fail_loudly():
     for kw in (dict(gcn_edge_feature="matrix"), dict(gcn_edge_type="learned"), dict(gcn_vertex_activation="relu"),
                dict(gcn_embed_dim=512)):
