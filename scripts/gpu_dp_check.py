@@ -35,7 +35,7 @@ def main():
     shard = [t[rank * bl:(rank + 1) * bl].contiguous().to(dev) for t in batch]
     tr = drin_b200.Trainer(model(), lr=1e-3, margin=cfg.triplet_margin)
     loss = tr.forward_backward(shard)
-    g_dp = tr.model.flat_grads.clone()
+    g_dp = tr.model.flat_grads[:tr.model.n_live].clone()      # live gradients (the tail slot carries the summed loss)
     tr.opt.step()
     scores_all = tr.rank_scores(shard, gather=True)
     res = {}
@@ -49,7 +49,8 @@ def main():
         from drin_b200.loss import triplet_loss_sharded
         l_ref, ds = triplet_loss_sharded(s, full[-1], cfg.triplet_margin)
         m._engine.backward(ctx, tuple(full[:-1]), params, ds, m._grad_views())
-        g_ref = m.flat_grads
+        g_ref = m.flat_grads[:m.n_live]
+        m._flat_grads_valid = True                 # the engine pieces were called directly (what Trainer does)
         res["loss_err"] = abs(float(loss) - float(l_ref)) / abs(float(l_ref))
         res["grad_err"] = float((g_dp - g_ref).abs().max() / g_ref.abs().max())
         ref.opt.step()

@@ -27,6 +27,9 @@ METRICS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__cluster_size",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__cycles_active.avg", "sm__inst_executed_pipe_uniform.sum",
+    "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_active",
+    "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
 ]
 
 
