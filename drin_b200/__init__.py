@@ -8,9 +8,10 @@ from .loss import TripletLoss, TopkAccuracy  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .trainer import Evaluator, GraphedStoreStep, HostFeeder, Trainer  # noqa: F401
 from .store import FeatureStore, IndexedBatch  # noqa: F401
+from .fit import evaluate, fit  # noqa: F401
 
 __all__ = ["Model", "TripletLoss", "TopkAccuracy", "FusedAdam", "Trainer", "Evaluator", "GraphedStoreStep", "HostFeeder", "FeatureStore", "IndexedBatch",
-           "install_as_reference_module"]
+           "fit", "evaluate", "install_as_reference_module"]
 
 
 def install_as_reference_module() -> None:

@@ -24,5 +24,11 @@ cap "$BASE" score_warp 1 1 prof_score_fwd
 # bf16 mode: the single-pass GEMMs of one train step (configs[3])
 python bench.py $BASE --precision bf16 > gpurun_out/plain_bf16.log 2>&1 && cap "$BASE --precision bf16" gemm_tcgen05 21 21 prof_gemm_bf16
 # WikiMEL shape: front end (the 12.4 MB / mention stream) and the ranking GEMMs (configs[2])
-python bench.py $BASE --dataset wikimel > gpurun_out/plain_wm.log 2>&1 && { cap "$BASE --dataset wikimel" frontend_kernel 1 1 prof_frontend_wm; cap "$BASE --dataset wikimel" gcn_layer_fwd_warp 2 2 prof_layer_fwd_wm; }
-ls -la gpurun_out | head -50
+python bench.py $BASE --dataset wikimel > gpurun_out/plain_wm.log 2>&1 && cap "$BASE --dataset wikimel" frontend_kernel 1 1 prof_frontend_wm
+# summarise on the box (only gpurun_out/ travels back, <= 64 MiB): tables -> gpurun_out/profiles_r02/, then drop the big reports
+DRIN_PROFILE_OUT=gpurun_out/profiles_r02 python scripts/summarize_profiles.py r02 "bench.py $BASE (1 warm-up + 2 timed + 3 event-profiled train steps, ranking passes), 4096 WikiDiverse mentions, fp32-parity"
+for r in prof_gemm prof_gemm_bf16 prof_frontend prof_score_bwd; do
+  ncu -i gpurun_out/$r.ncu-rep --page details --csv > gpurun_out/profiles_r02/${r}_details.csv 2>/dev/null
+done
+rm -f gpurun_out/prof_gemm.ncu-rep gpurun_out/prof_gemm_bf16.ncu-rep gpurun_out/prof_layer_fwd.ncu-rep gpurun_out/prof_layer0_bwd_col.ncu-rep gpurun_out/prof_frontend_wm.ncu-rep
+du -sh gpurun_out; ls gpurun_out/profiles_r02

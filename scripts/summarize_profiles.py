@@ -18,7 +18,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = os.environ.get("DRIN_PROFILE_OUT", os.path.join(ROOT, "profiles"))     # on the GPU box: a directory under gpurun_out/
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
