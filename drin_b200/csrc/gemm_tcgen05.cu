@@ -36,10 +36,16 @@ static constexpr int B_PLANE_BYTES = BN * BK * 2;   // 32 KB (16 KB per CTA in c
 static constexpr int ACC_STAGES = 2;
 static constexpr int TMEM_COLS = ACC_STAGES * BN;   // 512
 static constexpr int MAX_STAGES = 6;
-static constexpr int GEMM_THREADS = 192;
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue.  EIGHT epilogue warps: two per TMEM lane quarter
+// (a warp may only read the quarter warp_id % 4), the first four take columns 0..127 of the 256-column accumulator,
+// the other four columns 128..255.  With four warps the store path of a 128 x 256 tile (128 KB of fp32 per CTA) was
+// on the critical path of the single-pass (bf16 mode) and K = 768 GEMMs: 126 us vs 84 us without stores at
+// M = 90112, N = K = 768 (scripts/gemm_bf16_probe.py).
+static constexpr int EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 static constexpr int SMEM_TILE_BYTES = 192 * 1024;
-static constexpr int EPI_LD = 36;                                    // padded row (floats) of the epilogue transpose
-static constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_LD * 4;          // 4 epilogue warps x 32 rows
+static constexpr int EPI_LD = 32;                                    // staging row (floats): XOR-swizzled, no padding
+static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;  // one 32 x 32 fp32 staging tile per epilogue warp
 static constexpr int SMEM_TOTAL_BYTES = SMEM_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 struct GemmKernelParams {
@@ -198,7 +204,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * CTAS);     // one arrive per epilogue warp of every CTA of the pair
+      mbar_init(tempty_bar(a), EPI_WARPS * CTAS);     // one arrive per epilogue warp of every CTA of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -336,8 +342,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else {
-    // ================================ epilogue (4 warps, own 128 accumulator rows) ==========================
+    // ================================ epilogue (8 warps: 4 lane quarters x 2 column halves) =================
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;                   // column half of the 256-column accumulator (0 | 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = worker; t < total_tiles; t += nworkers) {
@@ -345,8 +352,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       tile_coords(t, m_blk, n_blk, ks);
       mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, 4);
       tcgen05_fence_after();
-      // Each thread owns one accumulator row in TMEM (32x32b shape); a padded smem transpose turns
-      // that into row-contiguous 128-B global stores (4 rows x 128 B per warp instruction).
+      // Each thread owns one accumulator row in TMEM (32x32b shape); an XOR-swizzled 32 x 32 smem transpose (float4
+      // slot s of row r lives at slot s ^ (r & 7): conflict-free both ways, no padding) turns that into row-contiguous
+      // 128-B global stores (4 rows x 128 B per warp instruction).
       const long long row_base = ((long long)m_blk * CTAS + cta_rank) * BM + q * 32;
       float* stg = reinterpret_cast<float*>(smem_raw + (stage_smem - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
       const int sub = lane >> 3, l8 = lane & 7;
@@ -366,7 +374,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       auto store_chunk = [&](int chunk, const uint32_t (&v)[32]) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(stg + lane * EPI_LD + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * EPI_LD + ((((i >> 2) ^ lane) & 7) << 2)) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         __syncwarp();
         const int ccol = chunk * 32 + 4 * l8;                         // column inside the tile
         const int col = n_blk * BN + ccol;
@@ -384,7 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + sub;
-            float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * l8);
+            float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + (((l8 ^ r) & 7) << 2));
             f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
             if (r < rows_valid) {
               if (c_ptr) *reinterpret_cast<float4*>(c_ptr + (long long)it * 4 * p.ldc + chunk * 32) = f;
@@ -402,7 +410,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + sub;
             const long long row = row_base + r;
-            float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * l8);
+            float4 f = *reinterpret_cast<const float4*>(stg + r * EPI_LD + (((l8 ^ r) & 7) << 2));
             f.x += bv.x; f.y += bv.y; f.z += bv.z; f.w += bv.w;
             const float ff[4] = {f.x, f.y, f.z, f.w};
             if (r < rows_valid) {
@@ -421,41 +429,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         __syncwarp();
       };
 
-      uint32_t va[32], vb[32];
-      if (nchunks > 0) tmem_ld_32x32(taddr0, va);
-#pragma unroll 1
-      for (int chunk = 0; chunk < nchunks; chunk += 2) {
-        tmem_ld_wait();                                                // va = chunk
-        if (chunk + 1 < nchunks) tmem_ld_32x32(taddr0 + (uint32_t)((chunk + 1) * 32), vb);
-        else {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CTAS == 1) mbar_arrive(tempty_bar(acc));
-            else mbar_arrive_cluster(tempty_bar(acc), 0u);            // the leader's MMA thread waits for both CTAs
-          }
-        }
-        store_chunk(chunk, va);
-        if (chunk + 1 < nchunks) {
-          tmem_ld_wait();                                              // vb = chunk + 1
-          if (chunk + 2 < nchunks) tmem_ld_32x32(taddr0 + (uint32_t)((chunk + 2) * 32), va);
-          else {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CTAS == 1) mbar_arrive(tempty_bar(acc));
-              else mbar_arrive_cluster(tempty_bar(acc), 0u);
-            }
-          }
-          store_chunk(chunk + 1, vb);
-        }
-      }
-      if (nchunks <= 0) {                                              // cannot happen (tiles start inside N); keep the protocol live
+      // this warp's chunks: column half `chalf` of the accumulator, clipped to the columns that exist
+      const int cbeg = chalf * (BN / 64);
+      const int cend = nchunks < cbeg + BN / 64 ? nchunks : cbeg + BN / 64;
+      auto release_acc = [&]() {                                       // this warp has read all it needs from TMEM
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (CTAS == 1) mbar_arrive(tempty_bar(acc));
-          else mbar_arrive_cluster(tempty_bar(acc), 0u);
+          else mbar_arrive_cluster(tempty_bar(acc), 0u);               // the leader's MMA thread waits for both CTAs
+        }
+      };
+      uint32_t va[32], vb[32];
+      if (cbeg < cend) tmem_ld_32x32(taddr0 + (uint32_t)(cbeg * 32), va);
+      else release_acc();                                              // ragged last N tile: nothing in this half
+#pragma unroll 1
+      for (int chunk = cbeg; chunk < cend; chunk += 2) {
+        tmem_ld_wait();                                                // va = chunk
+        if (chunk + 1 < cend) tmem_ld_32x32(taddr0 + (uint32_t)((chunk + 1) * 32), vb);
+        else release_acc();
+        store_chunk(chunk, va);
+        if (chunk + 1 < cend) {
+          tmem_ld_wait();                                              // vb = chunk + 1
+          if (chunk + 2 < cend) tmem_ld_32x32(taddr0 + (uint32_t)((chunk + 2) * 32), va);
+          else release_acc();
+          store_chunk(chunk + 1, vb);
         }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }

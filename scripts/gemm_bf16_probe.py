@@ -40,10 +40,13 @@ def run(layout, M, N, K, planes, out):
           f"{2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s algorithmic", flush=True)
 
 
+
 for out in ("f32", "bf16", "both"):
     run(0, 90112, 768, 768, 1, out)
-for out in ("f32", "bf16"):
-    run(0, 45056, 768, 2048, 1, out)
-    run(1, 90112, 768, 768, 1, out)
-run(0, 90112, 768, 768, 2, "f32")
-run(0, 8192, 768, 768, 1, "f32")
+run(0, 45056, 768, 2048, 1, "f32")
+run(1, 90112, 768, 768, 1, "f32")
+for out in ("f32", "both"):
+    run(0, 90112, 768, 768, 2, out)
+run(0, 45056, 768, 2048, 2, "f32")
+run(1, 90112, 768, 768, 2, "f32")
+run(0, 8192, 768, 768, 2, "both")
