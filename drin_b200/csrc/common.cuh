@@ -101,6 +101,33 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
   g = x * cdf;
   dg = fmaf(x * 0.3989422804014327f, ex, cdf);
 }
+// Packed-fp32 (FFMA2 / FMUL2, sm_100 `fma.rn.f32x2`) form of gelu_both for two elements at once.  The FMA pipe is not
+// faster per flop (scripts/ubench/fp32_pipe.cu: 70.8 vs 73.2 TFLOP/s) but a packed instruction takes ONE issue slot for
+// two results, and the row kernels are issue-bound.  Every lane-element goes through exactly the same
+// round-to-nearest operations as the scalar version: bit-identical results.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void gelu_both2(float2 x, float2& g, float2& dg) {
+  const float2 u = __fmul2_rn(f2(fabsf(x.x), fabsf(x.y)), f2(0.70710678118654752f));
+  const float2 den = __ffma2_rn(f2(0.3275911f), u, f2(1.0f));
+  const float2 t = f2(rcp_ftz(den.x), rcp_ftz(den.y));
+  const float2 e = __fmul2_rn(__fmul2_rn(x, x), f2(-0.72134752044448170f));
+  const float2 ex = f2(exp2_ftz(e.x), exp2_ftz(e.y));
+  float2 poly = __ffma2_rn(t, f2(1.061405429f), f2(-1.453152027f));
+  poly = __ffma2_rn(t, poly, f2(1.421413741f));
+  poly = __ffma2_rn(t, poly, f2(-0.284496736f));
+  poly = __ffma2_rn(t, poly, f2(0.254829592f));
+  const float2 npt = __fmul2_rn(f2(-poly.x, -poly.y), t);               // (-poly) * t, as the scalar code
+  const float2 erf_abs = __ffma2_rn(npt, ex, f2(1.0f));
+  const float2 cdf = __ffma2_rn(f2(0.5f), f2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y)), f2(0.5f));
+  g = __fmul2_rn(x, cdf);
+  dg = __ffma2_rn(__fmul2_rn(x, f2(0.3989422804014327f)), ex, cdf);
+}
+__device__ __forceinline__ float2 gelu_f2(float2 x) {
+  float2 g, dg;
+  gelu_both2(x, g, dg);
+  return g;
+}
 __device__ __forceinline__ float gelu_f(float x) {
   float g, dg;
   gelu_both(x, g, dg);

@@ -57,30 +57,32 @@ __device__ __forceinline__ float row_dot(const RowT<D>& a, const float* __restri
   return acc;
 }
 
-// y = gelu(LayerNorm(h)) in place (eps 1e-5, biased variance, like nn.LayerNorm); gamma/beta in smem
+// y = gelu(LayerNorm(h)) in place (eps 1e-5, biased variance, like nn.LayerNorm); gamma/beta in smem.
+// Packed fp32 (two elements per instruction, see gelu_both2); the row sums run as two interleaved partial sums
+// (even / odd elements) that are added before the warp reduction.
 template <int D>
 __device__ __forceinline__ void row_ln_gelu(RowT<D>& r, const float* __restrict__ gamma, const float* __restrict__ beta,
                                             int lane) {
-  float s = 0.f;
+  float2 s2 = f2(0.f);
 #pragma unroll
-  for (int i = 0; i < RowT<D>::NV * 4; ++i) s += r.v[i];
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
+  for (int i = 0; i < RowT<D>::NV * 4; i += 2) s2 = __fadd2_rn(s2, f2(r.v[i], r.v[i + 1]));
+  const float mean = warp_sum(s2.x + s2.y) * (1.0f / D);
+  float2 q2 = f2(0.f);
+  const float2 nmean = f2(-mean);
 #pragma unroll
-  for (int i = 0; i < RowT<D>::NV * 4; ++i) {
-    const float d = r.v[i] - mean;
-    q += d * d;
+  for (int i = 0; i < RowT<D>::NV * 4; i += 2) {
+    const float2 d = __fadd2_rn(f2(r.v[i], r.v[i + 1]), nmean);
+    q2 = __ffma2_rn(d, d, q2);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
-  const float shift = -mean * rstd;                        // xhat = h * rstd + shift: one FFMA per element
+  const float rstd = rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / D) + 1e-5f);
+  const float2 rs = f2(rstd), sh = f2(-mean * rstd);       // xhat = h * rstd + shift: one FMA per element
 #pragma unroll
   for (int j = 0; j < RowT<D>::NV; ++j) {
     const float4 g = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
     const float4 b = *reinterpret_cast<const float4*>(beta + (j * 32 + lane) * 4);
-    r.v[4 * j] = gelu_f(fmaf(fmaf(r.v[4 * j], rstd, shift), g.x, b.x));
-    r.v[4 * j + 1] = gelu_f(fmaf(fmaf(r.v[4 * j + 1], rstd, shift), g.y, b.y));
-    r.v[4 * j + 2] = gelu_f(fmaf(fmaf(r.v[4 * j + 2], rstd, shift), g.z, b.z));
-    r.v[4 * j + 3] = gelu_f(fmaf(fmaf(r.v[4 * j + 3], rstd, shift), g.w, b.w));
+    const float2 y0 = gelu_f2(__ffma2_rn(__ffma2_rn(f2(r.v[4 * j], r.v[4 * j + 1]), rs, sh), f2(g.x, g.y), f2(b.x, b.y)));
+    const float2 y1 = gelu_f2(__ffma2_rn(__ffma2_rn(f2(r.v[4 * j + 2], r.v[4 * j + 3]), rs, sh), f2(g.z, g.w), f2(b.z, b.w)));
+    r.v[4 * j] = y0.x; r.v[4 * j + 1] = y0.y; r.v[4 * j + 2] = y1.x; r.v[4 * j + 3] = y1.y;
   }
 }
 
