@@ -35,7 +35,12 @@ def gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
         return local
     world = dist.get_world_size(group)
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    if dist.get_backend(group) == "gloo":         # CPU / single-device test setups: gloo gathers host tensors only
+        host = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather(list(host.chunk(world)), local.detach().cpu().contiguous(), group=group)
+        out.copy_(host)
+    else:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
     return out
 
 

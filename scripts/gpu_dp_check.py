@@ -16,9 +16,17 @@ from oracle import drin_oracle as O  # noqa: E402  (weights init only)
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # DRIN_DP_SAME_DEVICE=1: every rank on cuda:0 over gloo -- the same data-parallel protocol through the same CUDA
+    # kernels on a box with ONE GPU (NCCL cannot put two ranks on one device)
+    same_device = os.environ.get("DRIN_DP_SAME_DEVICE", "0") == "1"
+    if same_device:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if same_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     dataset, cands = ("wikidiverse", 10)
     edge_feature = sys.argv[1] if len(sys.argv) > 1 else "scaler"
     B = 16 * world

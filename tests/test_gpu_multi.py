@@ -24,3 +24,20 @@ def test_two_gpu_step_equals_single_gpu_full_batch_step(edge_feature):
     assert line, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(line[-1][8:])
     assert res["loss_err"] < 1e-6 and res["grad_err"] < 1e-5 and res["rank_scores_err"] < 1e-5
+
+
+def test_two_ranks_on_one_gpu_equal_the_full_batch_step():
+    """The same check on a single-GPU box: two processes share cuda:0 and talk over gloo (NCCL refuses two ranks on one
+    device).  Everything but the transport is the product path: sharded forward, packed score / label all-gather, global
+    TripletLoss for the local rows, backward, ONE all-reduce over the live-gradient bucket with the loss share in its
+    tail, Adam, gathered ranking scores."""
+    env = dict(os.environ, DRIN_DP_SAME_DEVICE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "scripts", "gpu_dp_check.py"), "scaler"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in out.stdout.splitlines() if l.startswith("DPCHECK ")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(line[-1][8:])
+    assert res["world"] == 2
+    assert res["loss_err"] < 1e-6 and res["grad_err"] < 1e-5 and res["rank_scores_err"] < 1e-5
+    assert res["param_err_after_adam"] < 1e-6
