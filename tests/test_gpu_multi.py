@@ -41,3 +41,17 @@ def test_two_ranks_on_one_gpu_equal_the_full_batch_step():
     assert res["world"] == 2
     assert res["loss_err"] < 1e-6 and res["grad_err"] < 1e-5 and res["rank_scores_err"] < 1e-5
     assert res["param_err_after_adam"] < 5e-5          # Adam turns 1e-7 gradient noise into up to lr * noise / |g| on tiny entries
+
+
+def test_fit_data_parallel_equals_single_process_fit():
+    """drin_b200.fit with two ranks (one shared GPU, gloo) and a GLOBAL batch of 16 = the single-process fit of the same
+    schedule: same permutations, the loss of the global batch (scores all-gathered), gradients summed."""
+    env = dict(os.environ, DRIN_DP_SAME_DEVICE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29536", os.path.join(ROOT, "scripts", "gpu_fit_dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in out.stdout.splitlines() if l.startswith("FITCHECK ")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(line[-1][9:])
+    assert res["records"] == ["training", "validating", "testing"] * 2
+    assert res["loss_err"] < 1e-5 and res["param_err"] < 5e-4        # 10 Adam steps amplify 1e-7 gradient noise
