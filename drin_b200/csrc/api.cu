@@ -139,6 +139,7 @@ int drin_debug_option(const char* name, int32_t value) {
   else if (!strcmp(name, "vec_ctas_per_sm")) debug_set_vec_ctas_per_sm(value);
   else if (!strcmp(name, "gemm_sm_cap")) debug_set_gemm_sm_cap(value);
   else if (!strcmp(name, "workspace_guard")) debug_set_workspace_guard(value);
+  else if (!strcmp(name, "side_stream")) debug_set_side_stream(value);
   else return fail(DRIN_ERR_ARG, "drin_debug_option: unknown option '%s'", name);
   return DRIN_OK;
 }

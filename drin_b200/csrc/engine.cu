@@ -26,6 +26,54 @@ void debug_set_workspace_guard(int bytes) { g_guard_bytes = bytes > 0 ? align_up
 size_t debug_workspace_guard_bytes() { return g_guard_bytes; }
 const std::vector<size_t>& debug_workspace_guard_offsets() { return g_guard_offsets; }
 
+// ---- side stream (see engine.cuh) ----
+static bool g_side_stream = true;
+void debug_set_side_stream(int v) { g_side_stream = v != 0; }
+namespace {
+struct SideState {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  bool ok = false;
+};
+SideState g_side[64];
+}  // namespace
+
+SideStream::SideStream(cudaStream_t main) : main_(main) {
+  if (!g_side_stream || prof::enabled()) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  SideState& st = g_side[dev];
+  if (!st.ok) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;   // create outside captures
+    if (cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&st.fork_ev, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&st.join_ev, cudaEventDisableTiming) != cudaSuccess) return;
+    st.ok = true;
+  }
+  side_ = st.stream;
+  fork_ev_ = st.fork_ev;
+  join_ev_ = st.join_ev;
+}
+
+cudaStream_t SideStream::fork() {
+  if (!side_) return main_;
+  if (cudaEventRecord(fork_ev_, main_) != cudaSuccess || cudaStreamWaitEvent(side_, fork_ev_, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return main_;                      // cannot fork: stay serial (correct, just not concurrent)
+  }
+  forked_ = true;
+  return side_;
+}
+
+int SideStream::join() {
+  if (!side_ || !forked_) return DRIN_OK;
+  DRIN_CUDA(cudaEventRecord(join_ev_, side_));
+  DRIN_CUDA(cudaStreamWaitEvent(main_, join_ev_, 0));
+  forked_ = false;
+  return DRIN_OK;
+}
+
 namespace {
 struct Bump {
   char* base;
@@ -362,14 +410,35 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
   DRIN_TRY(frontend(stream, fa, bf16_in));
 
   // ---- input projections (ghmfc.py:66-69,250; model.py:42,45): x0 = [mt; mi; et; ei] ----
+  // The mention-side chain (W_mt, W_mi and, for a dynamic first layer, fu = W_u xm, beta = fu . b_v, g = fu W_v) only
+  // has 2B rows per GEMM: it runs on the side stream, in the shadow of the two candidate-side projections.
+  SideStream side(stream);
+  auto fu_chain = [&](cudaStream_t s, int l) -> int {      // model.py:149-150 for layer l (the W_v GEMM is folded)
+    LayerWs& lw = ws.layer[l];
+    const drin_layer_params& lp = p.layer[l];
+    GemmEpilogue ep;
+    ep.ldc = D; ep.ld_planes = D;
+    ep.C = lw.fu; ep.bias = lp.b_u; ep.out_hi = lw.fu_p.hi; ep.out_lo = lw.fu_p.lo;
+    DRIN_TRY(gemm_tcgen05(s, GEMM_NT, op(lw.xm_p, 2 * B, D), op(lw.w_u, D, D), 2 * B, D, D, ep));
+    DRIN_TRY(rowdot(s, D, lw.fu, 2 * B, lp.b_v, lw.beta_u));
+    GemmEpilogue eg;
+    eg.ldc = D; eg.C = lw.g;
+    return gemm_tcgen05(s, GEMM_NN, op(lw.fu_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, eg);
+  };
+  bool fu0_done = false;
   {
     GemmEpilogue ep;
     ep.ldc = D; ep.ld_planes = D;
+    cudaStream_t ms = side.fork();
     ep.C = ws.x0; ep.bias = p.b_mt; ep.out_hi = ws.xm0_p.hi; ep.out_lo = ws.xm0_p.lo;
-    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.span, B, D), op(ws.w_mt, D, D), B, D, D, ep));
+    DRIN_TRY(gemm_tcgen05(ms, GEMM_NT, op(ws.span, B, D), op(ws.w_mt, D, D), B, D, D, ep));
     ep.C = ws.x0 + B * D; ep.bias = p.b_mi; ep.out_hi = ws.xm0_p.hi + B * D;
     ep.out_lo = ws.xm0_p.lo ? ws.xm0_p.lo + B * D : nullptr;
-    DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.mim, B, R), op(ws.w_mi, D, R), B, D, R, ep));
+    DRIN_TRY(gemm_tcgen05(ms, GEMM_NT, op(ws.mim, B, R), op(ws.w_mi, D, R), B, D, R, ep));
+    if (side.on() && !ws.vec && ws.layer[0].dyn) {
+      DRIN_TRY(fu_chain(ms, 0));
+      fu0_done = true;
+    }
     ep.out_hi = ep.out_lo = nullptr;
     auto planes_at = [&](long long row) {          // vector edges: the candidate rows feed the W_v GEMM too
       if (!ws.vec) return;
@@ -382,6 +451,7 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
     ep.C = ws.x0 + (2 * B + BC) * D; ep.bias = p.b_ei;
     planes_at(2 * B + BC);
     DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.eimg, BC, R), op(ws.w_ei, D, R), BC, D, R, ep));
+    DRIN_TRY(side.join());
   }
   if (ws.vec) return forward_vector_layers(c, p, ws, scores, stream);
 
@@ -415,14 +485,7 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
     }
     la.xm = lw.xm;
     if (lw.dyn) {
-      GemmEpilogue ep;
-      ep.ldc = D; ep.ld_planes = D;
-      ep.C = lw.fu; ep.bias = lp.b_u; ep.out_hi = lw.fu_p.hi; ep.out_lo = lw.fu_p.lo;
-      DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(lw.xm_p, 2 * B, D), op(lw.w_u, D, D), 2 * B, D, D, ep));
-      DRIN_TRY(rowdot(stream, D, lw.fu, 2 * B, lp.b_v, lw.beta_u));
-      GemmEpilogue eg;
-      eg.ldc = D; eg.C = lw.g;
-      DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(lw.fu_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, eg));
+      if (!(l == 0 && fu0_done)) DRIN_TRY(fu_chain(stream, l));
       la.g = lw.g;
       la.beta_u = lw.beta_u;
       la.edges_out = lw.edges_out;

@@ -98,6 +98,25 @@ void debug_set_workspace_guard(int bytes);
 size_t debug_workspace_guard_bytes();
 const std::vector<size_t>& debug_workspace_guard_offsets();
 
+// Fork / join of ONE side stream per device, so that GEMMs without a data dependency run concurrently: a persistent
+// GEMM leaves SMs idle in its last, partially filled round of tiles (528 tile pairs over 74 CTA pairs = 7.13 rounds) and
+// the 2B-row GEMMs of the mention side fill a third of the machine; CTAs of an independent GEMM on the other stream take
+// those SMs as they free up.  The pattern (event recorded on the origin, waited on by the side stream, joined back) is
+// legal under CUDA-graph stream capture.  Off while the per-launch profiler runs (its event pairs assume serial launches).
+class SideStream {
+ public:
+  explicit SideStream(cudaStream_t main);
+  bool on() const { return side_ != nullptr; }
+  cudaStream_t fork();                 // side stream, ordered after everything enqueued on main so far (main if off)
+  int join();                          // main waits for everything enqueued on the side stream
+ private:
+  cudaStream_t main_;
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t fork_ev_ = nullptr, join_ev_ = nullptr;
+  bool forked_ = false;
+};
+void debug_set_side_stream(int v);
+
 int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace, size_t workspace_bytes,
             float* scores, cudaStream_t stream);
 int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, void* workspace,

@@ -216,6 +216,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
   if (ws.colsum_ctas != backward_ctas()) return fail(DRIN_ERR_ARG, "internal: partial-sum grid mismatch");
   const long long B = c.batch, C = c.candidates, BC = B * C;
   const int D = c.embed_dim, R = c.resnet_dim, L = c.gcn_layers;
+  SideStream side(stream);
   Deferred df;
   df.stream = stream; df.D = D;
   df.partial_next = ws.partial; df.partial_end = ws.partial + ws.partial_floats;
@@ -247,10 +248,14 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     }
     // dZ = dH W_h ; dW_h = dH^T Z
     {
+      // the two consumers of dH are independent: dW_h runs on the side stream next to dZ; joined before the layer
+      // kernel overwrites the dh planes with the gradient of the layer below
       GemmEpilogue ez;
       ez.C = ws.dz; ez.ldc = D;
+      cudaStream_t ss = side.fork();
+      DRIN_TRY(weight_grad(ss, ws, df, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dh, lw.rows, D), op(lw.w_h, D, D), lw.rows, D, D, ez));
-      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dh, lw.rows, D), op(lw.z, lw.rows, D), D, D, lw.rows, lg.w_h));
+      DRIN_TRY(side.join());
     }
     LayerBwdArgs la{};
     la.B = c.batch; la.C = c.candidates; la.D = D; la.full = lw.full;
@@ -299,13 +304,17 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
 
     if (lw.dyn) {
       // edge-update weights: fu = W_u xm + b_u, g = fu W_v, beta = fu . b_v
+      // four 2B-row GEMMs, each a third of the machine: the two weight gradients go to the side stream (dW_v needs
+      // only dg, dW_u the finished dfu planes), the data-gradient chain dfu -> dxu stays on the main stream
       GemmEpilogue ef;
       ef.C = ws.dfu; ef.ldc = D;
+      cudaStream_t ss = side.fork();
+      DRIN_TRY(weight_grad(ss, ws, df, op(lw.fu_p, 2 * B, D), op(ws.dg_p, 2 * B, D), D, D, 2 * B, lg.w_v));
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NT, op(ws.dg_p, 2 * B, D), op(lw.w_v, D, D), 2 * B, D, D, ef));
       DRIN_TRY(dfu_finish(stream, D, ws.dfu, ws.dbeta, lp.b_v, lw.fu, 2 * B, ws.dfu_p.hi, ws.dfu_p.lo, partC));
       DRIN_TRY(df.add_colsum(partC, backward_ctas(), nullptr, 0, 2, lg.b_u, lg.b_v, nullptr));
-      DRIN_TRY(weight_grad(stream, ws, df, op(lw.fu_p, 2 * B, D), op(ws.dg_p, 2 * B, D), D, D, 2 * B, lg.w_v));
-      DRIN_TRY(weight_grad(stream, ws, df, op(ws.dfu_p, 2 * B, D), op(lw.xm_p, 2 * B, D), D, D, 2 * B, lg.w_u));
+      ss = side.fork();                                    // the side stream now also waits for the dfu planes
+      DRIN_TRY(weight_grad(ss, ws, df, op(ws.dfu_p, 2 * B, D), op(lw.xm_p, 2 * B, D), D, D, 2 * B, lg.w_u));
       GemmEpilogue ex;
       ex.C = ws.dxu; ex.ldc = D;
       DRIN_TRY(gemm_tcgen05(stream, GEMM_NN, op(ws.dfu_p, 2 * B, D), op(lw.w_u, D, D), 2 * B, D, D, ex));
@@ -324,6 +333,7 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     }
     ma.partials = partB;
     DRIN_TRY(mention_bwd_finish(stream, ma));
+    DRIN_TRY(side.join());                                 // dg / dfu planes are rewritten by the layer below
     if (l > 0) {
       const drin_layer_params& pg = grads.layer[l - 1];
       DRIN_TRY(df.add_colsum(partA, rowsA, partB, backward_ctas(), 3, pg.ln_w, pg.ln_b, pg.b_h));
@@ -342,11 +352,16 @@ int backward(const drin_config& c, const drin_inputs& in, const drin_params& p, 
     DRIN_CUDA(cudaEventRecord(layers_done, stream));
   }
 
-  // input projections: dW = dX0^T A (no data gradient: the cached features are constants)
-  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, B, D, 0), op(ws.span, B, D), D, D, B, grads.w_mt));
-  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, B, D, B), op(ws.mim, B, R), D, R, B, grads.w_mi));
-  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, BC, D, 2 * B), op(ws.epool, BC, D), D, D, BC, grads.w_et));
-  DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, BC, D, 2 * B + BC), op(ws.eimg, BC, R), D, R, BC, grads.w_ei));
+  // input projections: dW = dX0^T A (no data gradient: the cached features are constants); the two mention-side ones
+  // (K = B rows) run beside the two candidate-side ones
+  {
+    cudaStream_t ss = side.fork();
+    DRIN_TRY(weight_grad(ss, ws, df, op(ws.dx0, B, D, 0), op(ws.span, B, D), D, D, B, grads.w_mt));
+    DRIN_TRY(weight_grad(ss, ws, df, op(ws.dx0, B, D, B), op(ws.mim, B, R), D, R, B, grads.w_mi));
+    DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, BC, D, 2 * B), op(ws.epool, BC, D), D, D, BC, grads.w_et));
+    DRIN_TRY(weight_grad(stream, ws, df, op(ws.dx0, BC, D, 2 * B + BC), op(ws.eimg, BC, R), D, R, BC, grads.w_ei));
+    DRIN_TRY(side.join());
+  }
   // every split-K slice and every per-CTA column partial of the pass is reduced here, in two launches
   DRIN_TRY(splitk_reduce_multi(stream, df.splitk));
   DRIN_TRY(colsum_reduce_multi(stream, df.colsum, D));

@@ -133,3 +133,33 @@ def test_evaluator_matches_the_reference_test_loop(tmp_path):
     path = tmp_path / "test-result.txt"
     ev.write_results(str(path), batch_size=6)
     assert path.read_text() == buf.getvalue()
+
+
+def test_side_stream_concurrency_does_not_change_a_bit():
+    """Independent GEMMs run on a forked side stream (csrc/engine.cu: SideStream): same kernels, same arguments, only the
+    schedule differs -- scores, loss and gradients must be bit-identical with the side stream off, at a size where the
+    GEMMs really overlap, and inside a captured CUDA graph (the fork / join is part of the capture)."""
+    import ctypes as C
+
+    from drin_b200 import _lib
+
+    def option(v):
+        _lib.check(_lib.load().drin_debug_option(b"side_stream", C.c_int32(v)), "drin_debug_option")
+
+    B, cands = 1500, 10
+    batch = make_batch("wikidiverse", B, 9, cands, device="cuda", generate_on_device=True)
+    outs = []
+    try:
+        for on in (1, 0, 1):
+            option(on)
+            tr = drin_b200.Trainer(_model(cands + 1))
+            loss = tr.forward_backward(batch)
+            rank = tr.rank_scores(batch)
+            torch.cuda.synchronize()
+            outs.append((loss.clone(), tr.last_scores.clone(), tr.model.flat_grads.clone(), rank.clone()))
+    finally:
+        option(1)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
