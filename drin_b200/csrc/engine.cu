@@ -361,6 +361,7 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
   const long long B = c.batch, C = c.candidates, BC = B * C;
   const int D = c.embed_dim, R = c.resnet_dim, L = c.gcn_layers;
 
+  SideStream side(stream);
   // ---- weights -> bf16 planes (they change every optimizer step): one launch for all matrices ----
   {
     SplitJobs jobs;
@@ -381,7 +382,8 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
         }
       }
     }
-    DRIN_TRY(split_planes_multi(stream, jobs));
+    // the weight planes are not needed before the first GEMM: produced on the side stream, beside the front end
+    DRIN_TRY(split_planes_multi(side.fork(), jobs));
   }
 
   // ---- front end: pooling, edges, projection operands ----
@@ -408,11 +410,11 @@ int forward(const drin_config& c, const drin_inputs& in, const drin_params& p, v
   fa.ei_hi = own_eimg ? ws.eimg.hi : nullptr; fa.ei_lo = own_eimg ? ws.eimg.lo : nullptr;
   fa.edges = ws.edges0;
   DRIN_TRY(frontend(stream, fa, bf16_in));
+  DRIN_TRY(side.join());
 
   // ---- input projections (ghmfc.py:66-69,250; model.py:42,45): x0 = [mt; mi; et; ei] ----
   // The mention-side chain (W_mt, W_mi and, for a dynamic first layer, fu = W_u xm, beta = fu . b_v, g = fu W_v) only
   // has 2B rows per GEMM: it runs on the side stream, in the shadow of the two candidate-side projections.
-  SideStream side(stream);
   auto fu_chain = [&](cudaStream_t s, int l) -> int {      // model.py:149-150 for layer l (the W_v GEMM is folded)
     LayerWs& lw = ws.layer[l];
     const drin_layer_params& lp = p.layer[l];
