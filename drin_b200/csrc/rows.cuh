@@ -151,34 +151,39 @@ __device__ __forceinline__ void row_ln_gelu_bwd(const RowT<D>& h, RowT<D>& d, co
 }
 
 // Forward recompute for the backward kernels, done ONCE per row: h -> xhat (in place), a = gelu(y),
-// da = gelu'(y) with y = gamma * xhat + beta; returns rstd.
+// da = gelu'(y) with y = gamma * xhat + beta; returns rstd.  Packed fp32 like row_ln_gelu (same per-element arithmetic).
 template <int D>
 __device__ __forceinline__ float row_ln_gelu_recompute(RowT<D>& h, RowT<D>& act, RowT<D>& dact,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int lane) {
-  float s = 0.f;
+  float2 s2 = f2(0.f);
 #pragma unroll
-  for (int i = 0; i < RowT<D>::NV * 4; ++i) s += h.v[i];
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
+  for (int i = 0; i < RowT<D>::NV * 4; i += 2) s2 = __fadd2_rn(s2, f2(h.v[i], h.v[i + 1]));
+  const float mean = warp_sum(s2.x + s2.y) * (1.0f / D);
+  float2 q2 = f2(0.f);
+  const float2 nmean = f2(-mean);
 #pragma unroll
-  for (int i = 0; i < RowT<D>::NV * 4; ++i) {
-    const float t = h.v[i] - mean;
-    q += t * t;
+  for (int i = 0; i < RowT<D>::NV * 4; i += 2) {
+    const float2 t = __fadd2_rn(f2(h.v[i], h.v[i + 1]), nmean);
+    q2 = __ffma2_rn(t, t, q2);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
-  const float shift = -mean * rstd;
+  const float rstd = rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / D) + 1e-5f);
+  const float2 rs = f2(rstd), sh = f2(-mean * rstd);
 #pragma unroll
   for (int j = 0; j < RowT<D>::NV; ++j) {
     const int off = (j * 32 + lane) * 4;
     const float4 g = *reinterpret_cast<const float4*>(gamma + off);
     const float4 b = *reinterpret_cast<const float4*>(beta + off);
-    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+    const float2 gg[2] = {f2(g.x, g.y), f2(g.z, g.w)}, bb[2] = {f2(b.x, b.y), f2(b.z, b.w)};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float xh = fmaf(h.v[4 * j + k], rstd, shift);
-      h.v[4 * j + k] = xh;
-      gelu_both(fmaf(xh, gg[k], bb[k]), act.v[4 * j + k], dact.v[4 * j + k]);
+    for (int k = 0; k < 2; ++k) {
+      const int i = 4 * j + 2 * k;
+      const float2 xh = __ffma2_rn(f2(h.v[i], h.v[i + 1]), rs, sh);
+      h.v[i] = xh.x; h.v[i + 1] = xh.y;
+      float2 a, da;
+      gelu_both2(__ffma2_rn(xh, gg[k], bb[k]), a, da);
+      act.v[i] = a.x; act.v[i + 1] = a.y;
+      dact.v[i] = da.x; dact.v[i + 1] = da.y;
     }
   }
   return rstd;
