@@ -90,3 +90,31 @@ def test_fuzzed_train_step_matches_oracle(case):
     finally:
         for name in OPTIONS:
             _lib.check(lib.drin_debug_option(name.encode(), C.c_int32(-1)), "drin_debug_option")
+
+
+@pytest.mark.parametrize("dataset,B,cands,kw", [
+    ("wikidiverse", 5, 6, dict(mention_objects=1, regions=7, entity_objects=1)),
+    ("wikidiverse", 9, 10, dict(mention_objects=4, regions=1, entity_objects=2)),
+    ("wikimel", 4, 7, dict(mention_objects=2, regions=16, entity_objects=2, entity_tokens=8, mention_tokens=32)),
+    ("wikimel", 1300, 2, dict(mention_objects=3, regions=3, entity_objects=1, entity_tokens=4, mention_tokens=32)),
+], ids=["wd_om1_p7", "wd_om4_p1_oe2", "wm_om2_p16_oe2", "wm_b1300_c3_tiny"])
+def test_object_and_region_counts_other_than_the_defaults(dataset, B, cands, kw):
+    """The loader's shapes are configuration (args.py:53,57: 49 regions, top-3 mention objects, 1 entity object); the
+    kernels take them from the batch like the reference's tensor code does: 1..4 mention objects, any region count,
+    several entity objects (model.py:78-92 loops over both), at a batch that dispatches the full-size kernels too."""
+    cfg = O.DrinConfig(num_candidates_model=cands + 1)
+    batch = make_batch(dataset, B, 77, cands, **kw)
+    sd = spread_weights(O.init_state(cfg, 0))
+    s_ref, l_ref, g_ref = O.train_step_grads(sd, batch[:-1], batch[-1], cfg)
+    model = drin_b200.Model(num_candidates_model=cands + 1)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    db = [t.cuda() for t in batch]
+    scores = model(db[:-1])
+    loss = drin_b200.TripletLoss(cfg.triplet_margin)(db[-1], scores)
+    loss.backward()
+    assert rel_err(scores.detach().cpu(), s_ref) < 1e-4
+    assert abs(float(loss) - float(l_ref)) <= 1e-4 * abs(float(l_ref)) + 1e-7
+    for k, p in model.named_parameters():
+        if g_ref[k] is not None:
+            assert rel_err(p.grad.cpu(), g_ref[k]) < 1e-4, k
