@@ -3,9 +3,10 @@ BASELINE INFRASTRUCTURE, never imported by the product (``drin_b200/``).
 
     python oracle/make_ref.py          # run in the build container (needs /root/reference)
 
-The reference is pure Python: "building" it means staging the four files the DRIN path imports
-(``drin/model.py`` -> ``common/args.py``, ``baselines/ghmfc.py``; ``common/utils.py`` for TripletLoss / TopkAccuracy)
-byte for byte under ``oracle/_ref/``.  That directory is git-ignored (reference sources never enter this repository's
+The reference is pure Python: "building" it means staging the files of the DRIN path
+(``drin/model.py`` -> ``common/args.py``, ``baselines/ghmfc.py``; ``common/utils.py`` for TripletLoss / TopkAccuracy) and
+its two callers (``train.py``, ``drin/data.py``: the entry point and the loader, executed unmodified by
+``tests/test_reference_train_py.py``) byte for byte under ``oracle/_ref/``.  That directory is git-ignored (reference sources never enter this repository's
 history) but not gpurun-ignored, so it travels to the GPU box, where ``/root/reference`` does not exist:
 ``bench.py --impl reference`` and ``cpu_baseline`` then time the reference's own code (``kind: "reference"``) instead of
 the oracle port, and ``tests/test_reference_glue.py`` drives ``drin_b200.Model()`` under the reference's real
@@ -22,7 +23,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("DRIN_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
-FILES = ("drin/model.py", "baselines/ghmfc.py", "common/args.py", "common/utils.py", "LICENSE")
+FILES = ("drin/model.py", "baselines/ghmfc.py", "common/args.py", "common/utils.py", "drin/data.py", "train.py", "LICENSE")
 
 
 def stage(verbose: bool = True) -> bool:
