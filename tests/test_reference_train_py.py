@@ -21,21 +21,34 @@ from tests.test_store import write_cache_dir
 
 HAVE = ref_import.available() and os.path.isfile(os.path.join(ref_import.REFERENCE_ROOT, "train.py"))
 needs_ref = pytest.mark.skipif(not HAVE, reason="reference train.py / drin/data.py not staged (python oracle/make_ref.py)")
-CANDS = 10
 
 
-def _write_splits(root):
+ENTITY_TABLES = ("entity_text_feature", "entity_text_mask", "entity_image_feature", "entity_object_feature",
+                 "entity_object_score")
+SHAPES = {"wikidiverse": dict(cands=10, le=64, kw={}),
+          # WikiMEL layout: one entity table shared by the splits, candidates found through qid2idx (drin/data.py:88-93)
+          "wikimel": dict(cands=5, le=16, kw=dict(num_entities=24, entity_tokens=16, mention_tokens=32))}
+
+
+def _write_splits(root, dataset):
+    sh = SHAPES[dataset]
+    shared = None
     for split, n, seed in (("train", 20, 1), ("valid", 8, 2), ("test", 8, 3)):       # 20 = 2 x 8 + 4: a short last batch
-        write_cache_dir(root, "wikidiverse", synthetic_tables("wikidiverse", n, seed, CANDS), split, CANDS + 1)
+        t = synthetic_tables(dataset, n, seed, sh["cands"], **sh["kw"])
+        if dataset == "wikimel":
+            shared = shared or {k: t[k] for k in ENTITY_TABLES}
+            t.update(shared)
+        write_cache_dir(root, dataset, t, split, sh["cands"] + 1)
 
 
-def _run_reference_main(root, cuda_model: bool):
+def _run_reference_main(root, cuda_model: bool, dataset="wikidiverse"):
     """Import the reference's train.py under a patched common.args and run main(); returns (model, stdout)."""
     sys.modules.pop("train", None)
-    ref_import.load("wikidiverse", CANDS, 64, preprocess_dir=root, mention_mmap=None, entity_mmap=None,
+    sh = SHAPES[dataset]
+    ref_import.load(dataset, sh["cands"], sh["le"], preprocess_dir=root, mention_mmap=None, entity_mmap=None,
                     dataloader_workers=0, batch_size=8, shuffle_train_data=False, num_epoch=2, test_epoch_interval=1,
                     use_device="cuda" if cuda_model else "cpu", output_test_result=False, profiling=False, debug=False,
-                    test_only=False, seed=0, model_type="drin")
+                    test_only=False, seed=0, model_type="drin", metrics_topk=[1, 3, 5], acc_correction=[0, 0, 0])
     lightning_stub.install()
     if cuda_model:
         drin_b200.install_as_reference_module()          # INTEGRATION.md section 1 (a)
@@ -66,7 +79,7 @@ def _logged(text):
 @needs_ref
 def test_stub_runs_the_reference_entry_point_on_cpu(tmp_path):
     root = str(tmp_path) + os.sep
-    _write_splits(root)
+    _write_splits(root, "wikidiverse")
     model, text = _run_reference_main(root, cuda_model=False)
     losses, top1 = _logged(text)
     # 2 blocks x (3 train + 1 valid + 1 test) steps, banners of EpochLogger, the closing line of main()
@@ -77,11 +90,12 @@ def test_stub_runs_the_reference_entry_point_on_cpu(tmp_path):
 
 @needs_ref
 @pytest.mark.gpu
-def test_reference_train_py_runs_unmodified_on_the_cuda_module(tmp_path):
+@pytest.mark.parametrize("dataset", ["wikidiverse", "wikimel"])
+def test_reference_train_py_runs_unmodified_on_the_cuda_module(tmp_path, dataset):
     root = str(tmp_path) + os.sep
-    _write_splits(root)
-    ref_model, ref_text = _run_reference_main(root, cuda_model=False)
-    our_model, our_text = _run_reference_main(root, cuda_model=True)
+    _write_splits(root, dataset)
+    ref_model, ref_text = _run_reference_main(root, cuda_model=False, dataset=dataset)
+    our_model, our_text = _run_reference_main(root, cuda_model=True, dataset=dataset)
     assert isinstance(our_model, drin_b200.Model) and next(our_model.parameters()).is_cuda
     (l_ref, t_ref), (l_our, t_our) = _logged(ref_text), _logged(our_text)
     assert len(l_ref) == len(l_our) == 10
