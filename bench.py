@@ -386,7 +386,9 @@ class Bench:
                "frontend_gbs": fe_gbs, "frontend_hbm_frac": fe_gbs / self.hbm_peak,
                "gemm_tflops": g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else None,
                "stage_ms_per_pass": {k: v["ms"] / n for k, v in prof.items() if v["ms"] > 0},
-               "algorithmic_bytes_per_mention": abytes, "clocks": clocks}
+               "algorithmic_bytes_per_mention": abytes, "clocks": clocks,
+               "l2": f"inputs {batch_bytes_per_mention('wikimel') * B / 2**30:.1f} GiB per pass per GPU, larger than the 126 MB "
+                     "L2 (no flush needed)", "steps": steps, "warmup": warmup}
         del model, tr, batch
         self.torch.cuda.empty_cache()
         return out
@@ -409,7 +411,9 @@ class Bench:
                "gemm_tflops": tf, "gemm_frac_of_tensor_peak": tf / self.tensor_peak,
                "stage_ms_per_step": {k: v["ms"] / n for k, v in prof.items() if v["ms"] > 0},
                "tolerance": "scores/loss 2e-3, gradients 3e-2 against the fp32 reference on bf16-rounded features "
-                            "(tests/test_gpu_parity_scale.py)", "clocks": clocks}
+                            "(tests/test_gpu_parity_scale.py)", "clocks": clocks,
+               "l2": f"inputs {batch_bytes_per_mention('wikidiverse', True) * B / 2**30:.1f} GiB per step per GPU, larger than "
+                     "the 126 MB L2 (no flush needed)", "steps": steps, "warmup": warmup}
         del model, tr, batch
         self.torch.cuda.empty_cache()
         return out
