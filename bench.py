@@ -393,11 +393,12 @@ class Bench:
         self.torch.cuda.empty_cache()
         return out
 
-    def leg_bf16_train(self, steps, warmup):
+    def leg_bf16_train(self, steps, warmup, dataset="wikidiverse"):
         """BASELINE configs[3]: data-parallel training with bf16 features (single-pass bf16 GEMMs), NCCL all-reduce at
-        N > 1; WikiDiverse shape, 4096 mentions per GPU."""
-        B = 4096
-        model, tr, batch = self.make("wikidiverse", B, bf16=True, seed=4000)
+        N > 1; WikiDiverse shape with 4096 mentions per GPU, WikiMEL shape (C=101, Le=64) with 576."""
+        wm = dataset == "wikimel"
+        B = 576 if wm else 4096
+        model, tr, batch = self.make(dataset, B, bf16=True, seed=4000)
         sampler = ClockSampler(self.local, self.rank == 0).start()
         ms = self.timed(lambda: tr.step(batch), steps, warmup)
         n = max(steps // 2, 3)
@@ -405,14 +406,15 @@ class Bench:
         clocks = sampler.stop()
         g = prof["gemm"]
         tf = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
-        out = {"config": "BASELINE configs[3]: DRIN data-parallel training, bf16 features, WikiDiverse shape (C=11), "
+        out = {"config": "BASELINE configs[3]: DRIN data-parallel training, bf16 features, "
+                         + ("WikiMEL shape (C=101, Le=64), " if wm else "WikiDiverse shape (C=11), ") +
                          f"{B} mentions per GPU per step, dp{self.world}" + (", NCCL grad all-reduce" if self.world > 1 else ""),
                "value": self.world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": B, "dtype": "bf16",
                "gemm_tflops": tf, "gemm_frac_of_tensor_peak": tf / self.tensor_peak,
                "stage_ms_per_step": {k: v["ms"] / n for k, v in prof.items() if v["ms"] > 0},
                "tolerance": "scores/loss 2e-3, gradients 3e-2 against the fp32 reference on bf16-rounded features "
                             "(tests/test_gpu_parity_scale.py)", "clocks": clocks,
-               "l2": f"inputs {batch_bytes_per_mention('wikidiverse', True) * B / 2**30:.1f} GiB per step per GPU, larger than "
+               "l2": f"inputs {batch_bytes_per_mention(dataset, True) * B / 2**30:.1f} GiB per step per GPU, larger than "
                      "the 126 MB L2 (no flush needed)", "steps": steps, "warmup": warmup}
         del model, tr, batch
         self.torch.cuda.empty_cache()
@@ -487,7 +489,8 @@ class Bench:
             k, w = max(args.steps // 2, 5), max(args.warmup, 3)
             del model, trainer
             torch.cuda.empty_cache()
-            legs = {"wikimel_ranking": self.leg_wikimel_ranking(k, w), "bf16_train": self.leg_bf16_train(k, w)}
+            legs = {"wikimel_ranking": self.leg_wikimel_ranking(k, w), "bf16_train": self.leg_bf16_train(k, w),
+                    "bf16_train_wikimel": self.leg_bf16_train(k, w, "wikimel")}
             if world == 1:
                 legs["sweep"] = self.leg_sweep()
 
