@@ -128,6 +128,12 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi needs a few hundred ms to come up: wait for its first line so that the samples cover the timed
+            # region that follows (a 150 ms region would otherwise see one sample or none), then drop the idle samples
+            t0 = time.perf_counter()
+            while not self.samples and time.perf_counter() - t0 < 2.0:
+                time.sleep(0.01)
+            self.samples.clear()
         except Exception:
             self.proc = None
         return self
