@@ -180,6 +180,7 @@ class Model(nn.Module):
                 off += n
         self._flat = flat
         self._flat_grad = None
+        self._flat_grads_valid = False      # set by Trainer once it has written the flat gradient buffer
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
