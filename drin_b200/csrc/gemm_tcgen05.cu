@@ -368,7 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       bf16* hi_ptr = p.out_hi ? p.out_hi + (row_base + sub) * p.ld_planes + n_blk * BN + 4 * l8 : nullptr;
       bf16* lo_ptr = p.out_lo ? p.out_lo + (row_base + sub) * p.ld_planes + n_blk * BN + 4 * l8 : nullptr;
 
-      // one chunk = 32 accumulator columns: registers -> padded smem transpose -> 128-B row segments in global.
+      // one chunk = 32 accumulator columns: registers -> swizzled smem transpose -> 128-B row segments in global.
       // The TMEM load of chunk i + 1 is issued before chunk i is stored, so its latency hides behind the stores;
       // once the last load has landed the accumulator is handed back to the MMA warp.
       auto store_chunk = [&](int chunk, const uint32_t (&v)[32]) {
