@@ -230,13 +230,13 @@ class WorkspacePool:
         if fit:
             e = fit[0]
         else:
-            done = sorted((e for e in mine if e not in free and self._lease_of(e).state == "done"
+            free_ids = {id(e) for e in free}           # identity, never ==: the entries are dicts holding tensors
+            done = sorted((e for e in mine if id(e) not in free_ids and self._lease_of(e).state == "done"
                            and e["ws"].numel() >= need), key=lambda e: e["ws"].numel())
             if done:
                 e = done[0]
-            else:
-                for old in free:                       # too small and unowned: let the allocator have it back
-                    self.entries.remove(old)
+            else:                                      # too small and unowned: let the allocator have them back
+                self.entries = [x for x in self.entries if id(x) not in free_ids]
                 e = dict(ws=torch.empty(need, dtype=torch.uint8, device=device), gen=0, lease=None)
                 self.entries.append(e)
         e["gen"] += 1

@@ -146,3 +146,26 @@ def test_vector_edge_model_is_a_drop_in_for_the_reference_constructor():
     assert dead == [f"gcn_layers.1.{s}" for s in ("w_m.weight", "w_m.bias", "w_u.weight", "w_u.bias", "w_v.weight",
                                                   "w_v.bias")]
     assert int(m.dead_mask().sum()) == 768 * 768 + 768 + 2 * (384 * 768 + 384)
+
+
+def test_workspace_pool_lease_semantics():
+    """Host logic of Engine.pool (no GPU needed): a live lease is never handed out again, a finished ('done') lease is
+    reclaimed by the next acquire and becomes invalid, released leases are reused, too-small free workspaces are dropped."""
+    pool = E.WorkspacePool()
+    dev = torch.device("cpu")
+    a = pool.acquire(1000, dev)
+    b = pool.acquire(500, dev)                      # a is live: a second workspace
+    assert a.entry is not b.entry and len(pool.entries) == 2 and a.valid() and b.valid()
+    b.release()
+    c = pool.acquire(400, dev)                      # reuses the released one (smallest that fits)
+    assert c.entry is b.entry and not b.valid() and c.valid()
+    a.state = "done"                                # what Engine.backward sets
+    assert a.valid()                                # a second backward right away is still fine
+    c.release()
+    d = pool.acquire(900, dev)                      # the free 500-byte one is too small: the done lease is reclaimed
+    assert d.entry is a.entry and not a.valid() and d.valid()
+    del d                                           # a dropped lease (autograd graph freed) frees its workspace
+    import gc
+    gc.collect()
+    e = pool.acquire(2000, dev)                     # nothing fits: the free ones are dropped, one new workspace
+    assert len(pool.entries) == 1 and pool.entries[0]["ws"].numel() == 2000 and e.valid()
