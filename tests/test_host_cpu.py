@@ -169,3 +169,18 @@ def test_workspace_pool_lease_semantics():
     gc.collect()
     e = pool.acquire(2000, dev)                     # nothing fits: the free ones are dropped, one new workspace
     assert len(pool.entries) == 1 and pool.entries[0]["ws"].numel() == 2000 and e.valid()
+
+
+def test_loss_scratch_cache_is_keyed_and_bounded():
+    """ADVICE r1 (loss.py:36): the scratch of one (B, C) must survive calls with other shapes (a CUDA graph holds raw
+    pointers into it); the cache is a small LRU, not a single slot."""
+    from drin_b200 import loss as L
+    L._scratch.clear()
+    a = L._loss_scratch(64, 11, "cpu")
+    b = L._loss_scratch(48, 11, "cpu")
+    assert L._loss_scratch(64, 11, "cpu") is a and L._loss_scratch(48, 11, "cpu") is b     # alternating shapes: no churn
+    for i in range(L._SCRATCH_KEEP + 3):
+        L._loss_scratch(100 + i, 11, "cpu")
+    assert len(L._scratch) == L._SCRATCH_KEEP and len(L.scratch_tensors()) == L._SCRATCH_KEEP
+    assert a.numel() > 0                       # evicted from the cache, still alive for whoever kept a reference
+    L._scratch.clear()
