@@ -55,6 +55,10 @@ def fit(model: Model, train: FeatureStore, valid: Optional[FeatureStore] = None,
         raise ValueError(f"the global batch size {batch_size} must be a multiple of the number of ranks {world}")
     gen = torch.Generator().manual_seed(seed)                      # same order on every rank
     history: List[Dict] = []
+    own_file = None
+    if isinstance(result_file, (str, bytes)) or hasattr(result_file, "__fspath__"):
+        # the reference opens test-result.txt once and every test pass appends to it (train.py:16-17,40-43,94-96)
+        own_file = result_file = open(result_file, "w") if rank == 0 else None
     say = log if (log is not None and rank == 0) else (lambda s: None)
     blocks = max(num_epoch // test_epoch_interval, 1)
     epoch = 0
@@ -84,7 +88,12 @@ def fit(model: Model, train: FeatureStore, valid: Optional[FeatureStore] = None,
                 loss_sum += loss.reshape(1)
                 metric.update(scores, labels)                               # train.py:36-37, device-side counters
                 steps += 1
-            acc = (metric.correct.double() / max(metric.total, 1) / (1.0 - acc_correction[0])).tolist()
+            correct, total = metric.correct, metric.total
+            if world > 1:                                                   # every rank counted its own shard
+                correct = correct.clone()
+                dist.all_reduce(correct, op=dist.ReduceOp.SUM, group=group)
+                total *= world
+            acc = (correct.double() / max(total, 1) / (1.0 - acc_correction[0])).tolist()
             rec = {"epoch": epoch, "type": "training", "loss": float(loss_sum) / max(steps, 1), "steps": steps,
                    "topk": dict(zip(metric.top_k, acc))}
             history.append(rec)
@@ -100,13 +109,14 @@ def fit(model: Model, train: FeatureStore, valid: Optional[FeatureStore] = None,
             ev = evaluate(model, test, batch_size, margin, top_k, keep_scores=result_file is not None)
             r = ev.compute(acc_correction[2])
             if result_file is not None and rank == 0:
-                if hasattr(result_file, "write"):
-                    result_file.write("==========  Test ==========\n")      # train.py:94-96
+                result_file.write("==========  Test ==========\n")          # train.py:94-96
                 ev.write_results(result_file, batch_size)
             rec = {"epoch": epoch, "type": "testing", "loss": r["loss"], "topk": r["topk"]}
             history.append(rec)
             say(f"***** Epoch {epoch}/{num_epoch} - testing - loss: {rec['loss']:.5f}\t" +
                 "\t".join(f"top-{k}: {a:.5f}" for k, a in rec["topk"].items()))
         del graphed
+    if own_file is not None:
+        own_file.close()
     say("Training completed")
     return history

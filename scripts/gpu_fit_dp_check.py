@@ -52,6 +52,7 @@ def main():
         res["loss_err"] = max(abs(a["loss"] - b["loss"]) / max(abs(b["loss"]), 1e-9)
                               for a, b in zip(hist_dp, hist_one) if a["type"] == b["type"] == "training")
         res["records"] = [r["type"] for r in hist_dp]
+        res["topk_err"] = max(abs(a["topk"][k] - b["topk"][k]) for a, b in zip(hist_dp, hist_one) for k in a["topk"])
         res["world"] = world
         print("FITCHECK " + json.dumps(res), flush=True)
     dist.barrier()

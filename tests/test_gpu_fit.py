@@ -30,7 +30,7 @@ def _model():
 
 
 @pytest.mark.parametrize("graph", [True, False], ids=["graphed", "eager"])
-def test_fit_equals_hand_written_reference_loop(graph):
+def test_fit_equals_hand_written_reference_loop(graph, tmp_path):
     train, valid, test = _stores()
     B, epochs, interval, corr = 16, 4, 2, (0.1, 0.2, 0.0)
     m1, m2 = _model(), _model()
@@ -62,3 +62,8 @@ def test_fit_equals_hand_written_reference_loop(graph):
     # result file: one banner per test pass, "{index}:\t[scores]\n{labels}\n" per mention (train.py:40-43,94-96)
     text = buf.getvalue()
     assert text.count("==========  Test ==========") == 2 and text.count(":\t[") == 2 * len(test)
+    if graph:       # a path instead of a file object: opened once, every test pass appends (train.py:16-17)
+        path = tmp_path / "test-result.txt"
+        drin_b200.fit(_model(), train, None, test, batch_size=B, num_epoch=2, test_epoch_interval=1, seed=5, graph=False,
+                      result_file=str(path), log=None)
+        assert path.read_text().count("==========  Test ==========") == 2

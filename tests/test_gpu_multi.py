@@ -55,3 +55,4 @@ def test_fit_data_parallel_equals_single_process_fit():
     res = json.loads(line[-1][9:])
     assert res["records"] == ["training", "validating", "testing"] * 2
     assert res["loss_err"] < 1e-5 and res["param_err"] < 5e-4        # 10 Adam steps amplify 1e-7 gradient noise
+    assert res["topk_err"] < 1e-9                                    # training accuracies are summed over the ranks' shards
