@@ -60,6 +60,7 @@ class FusedAdam:
                 p(flat), p(grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.skip), C.c_int64(flat.numel()),
                 p(self._step), C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]),
                 C.c_float(self.eps), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "drin_adam_step_dev")
+        m._flat_grads_valid = False        # consumed: the next step needs a new backward (Trainer or autograd)
 
     @property
     def step_count(self) -> int:
